@@ -1,0 +1,739 @@
+// K1 (tensor-core path) — fused TF32 scorer on tcgen05 with TMA-staged item tiles, TMEM accumulators,
+// an in-epilogue threshold filter, exact fp32 rescoring and a proven-margin check.
+//
+// Replaces MF.batch_predict (model/MF.py:58-63) + mask writes + torch.topk of _evaluate
+// (model/BaseRecommender.py:170-182) for d = 64.  The (B, I) score matrix never exists: scores live
+// only in TMEM and registers.
+//
+// One CTA = one "unit" = 256 queries (two 128-row A tiles, resident in shared memory for the whole
+// sweep) x one contiguous range of item tiles.  Warp roles (384 threads):
+//   warp 0      TMA producer: item tiles (128 items x 64 fp32 = two SWIZZLE_128B boxes) into a 4-stage ring
+//   warp 1      MMA issuer: 16 x tcgen05.mma kind::tf32 (M128 N128 K8) per tile into one of two TMEM stages
+//   warp 2      mask producer: per tile a 128-bit "do not take" bitmap per query (train items via a
+//               monotone cursor in the sorted CSR row, flagged items, items past the end) in shared memory
+//   warp 3      idle (owns the TMEM allocation)
+//   warps 4-11  epilogue: thread = one query (= one TMEM lane).  Per 32-column chunk: tcgen05.ld,
+//               3-input max tree, one compare against the query's running threshold (the KSEL-th best
+//               approximate score).  Only when some lane beats its threshold does the warp enter the
+//               cooperative slow path: the lane's 32 values are transposed through shared memory, each
+//               lane tests one column against threshold and bitmap, survivors are appended to the query's
+//               candidate buffer (global memory, L2 resident); a full buffer is rank-compacted by the warp.
+// After the sweep a second kernel re-scores every candidate in exact fp32 (k = 0..63 in order), selects
+// the top-K by (score desc, id asc) and proves the selection: every rejected item has approximate
+// score <= thr, hence exact score <= thr + eps with eps = 2^-8.9 |q| max|x| (TF32 operand truncation),
+// so the list is exact if its K-th exact score exceeds thr + eps.  Queries that fail the proof are
+// re-run by the exact fp32 scorer (score_simt.cu) in the same call.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kD = 64;                 // embedding width served by this path
+constexpr int kBM = 256;               // queries per unit (2 x 128-row MMA tiles)
+constexpr int kBN = 128;               // items per tile
+constexpr int kStages = 4;             // item smem ring
+constexpr int kAcc = 2;                // TMEM accumulator stages (2 x 256 columns)
+constexpr int kThreads = 384;
+constexpr int kEpiWarp0 = 4;           // first epilogue warp
+constexpr int kChunkBytes = 128 * 128; // one SWIZZLE_128B box: 128 rows x 32 fp32
+constexpr int kTileBytes = 2 * kChunkBytes;
+constexpr float kEpsFactor = 2.1e-3f;  // > 2^-9 * (1 + 2^-10) + fp32 accumulation slack, see header comment
+constexpr uint32_t kSpinLimit = 1u << 26;
+
+struct Cand {
+    float s;
+    int p;   // position in the local item table
+};
+
+// ---------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trap (launch failure) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > kSpinLimit) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row groups are
+// 1024 B apart (SBO), LBO unused for swizzled K-major, version 1, layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// kind::tf32 instruction descriptor: D=F32, A=B=TF32, both K-major, N=128, M=128.
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+// ---------------------------------------------------------------------------------------------- sweep
+struct SweepParams {
+    int64_t n_q;             // valid queries (rows of Q beyond it are TMA zero fill)
+    int n_q_pad;             // n_utiles * 256
+    int n_utiles;
+    int64_t n_items;
+    int tiles_per_split;
+    int n_tiles;             // ceil(n_items / 128)
+    const int32_t* item_gids;
+    int64_t item_id_base;
+    const int64_t* mask_rowptr;
+    const int32_t* mask_col;
+    const uint8_t* item_flags;
+    uint8_t flag_exclude;
+    Cand* buf;               // [S][n_q_pad][CAP]
+    int* cnt;                // [S][n_q_pad]
+    float* thr;              // [S][n_q_pad]
+    float* dbg_scores;       // optional: raw TF32 scores of the first 256 x 128 block (probe)
+};
+
+struct SmemLayout {
+    static constexpr int kA = 0;                                   // 2 utiles x 2 k-chunks x 16 KB
+    static constexpr int kB = kA + 4 * kChunkBytes;                // kStages x 32 KB
+    static constexpr int kMask = kB + kStages * kTileBytes;        // [kAcc][4 words][256 queries] u32
+    static constexpr int kCommon = kMask + kAcc * 4 * kBM * 4;     // [kAcc][4] u32
+    static constexpr int kScratch = kCommon + 64;                  // 8 warps x 32 floats
+    static constexpr int kBars = kScratch + 8 * 128;
+    static constexpr int kTotal = kBars + 256;
+};
+
+// Rank-compact one query's candidate buffer to its best KSEL entries, sorted; returns the KSEL-th score.
+template <int EPL>
+__device__ float warp_shrink(Cand* buf, int cnt, int ksel, int lane) {
+    Cand e[EPL];
+    int rank[EPL];
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        const int idx = lane + 32 * i;
+        e[i] = Cand{-CUDART_INF_F, 0x7fffffff};
+        if (idx < cnt) {
+            const float2 raw = __ldcg(reinterpret_cast<const float2*>(buf) + idx);
+            e[i] = Cand{raw.x, __float_as_int(raw.y)};
+        }
+        rank[i] = 0;
+    }
+    for (int j = 0; j < 32; ++j) {
+#pragma unroll
+        for (int i2 = 0; i2 < EPL; ++i2) {
+            const float s = __shfl_sync(CR_FULL_MASK, e[i2].s, j);
+            const int p = __shfl_sync(CR_FULL_MASK, e[i2].p, j);
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) rank[i] += cr::better(s, p, e[i].s, e[i].p) ? 1 : 0;
+        }
+    }
+    float thr = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        const bool keep = (lane + 32 * i < cnt) && rank[i] < ksel;
+        if (keep) reinterpret_cast<float2*>(buf)[rank[i]] = make_float2(e[i].s, __int_as_float(e[i].p));
+        const unsigned who = __ballot_sync(CR_FULL_MASK, keep && rank[i] == ksel - 1);
+        if (who) thr = __shfl_sync(CR_FULL_MASK, e[i].s, __ffs(who) - 1);
+    }
+    __syncwarp();
+    return thr;
+}
+
+template <int KSEL>
+__global__ void __launch_bounds__(kThreads, 1)
+score_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_i, const SweepParams p) {
+    constexpr int CAP = KSEL + 32;
+    constexpr int EPL = CAP / 32;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sA = smem + SmemLayout::kA;
+    unsigned char* sB = smem + SmemLayout::kB;
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(smem + SmemLayout::kMask);
+    uint32_t* sCommon = reinterpret_cast<uint32_t*>(smem + SmemLayout::kCommon);
+    float* sScratch = reinterpret_cast<float*>(smem + SmemLayout::kScratch);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SmemLayout::kBars);
+    uint64_t* full = bars;                      // [kStages]  TMA -> MMA
+    uint64_t* empty = bars + kStages;           // [kStages]  MMA -> TMA
+    uint64_t* tfull = bars + 2 * kStages;       // [kAcc]     MMA -> epilogue
+    uint64_t* tempty = tfull + kAcc;            // [kAcc]     epilogue -> MMA / mask producer
+    uint64_t* mfull = tempty + kAcc;            // [kAcc]     mask producer -> epilogue
+    uint64_t* afull = mfull + kAcc;             // [1]        query tiles landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int utile = blockIdx.x % p.n_utiles, split = blockIdx.x / p.n_utiles;
+    const int tile_begin = split * p.tiles_per_split;
+    const int tile_end = min(p.n_tiles, tile_begin + p.tiles_per_split);
+    const int n_local = tile_end - tile_begin;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < kAcc; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); mbar_init(&mfull[a], 1); }
+        mbar_init(afull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 3) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            mbar_expect_tx(afull, 4 * kChunkBytes);
+            for (int t = 0; t < 2; ++t)
+                for (int kc = 0; kc < 2; ++kc)
+                    tma_load_2d(sA + (t * 2 + kc) * kChunkBytes, &map_q, afull, kc * 32, utile * kBM + t * 128);
+            for (int i = 0; i < n_local; ++i) {
+                const int s = i % kStages;
+                if (i >= kStages) mbar_wait(&empty[s], ((i / kStages) - 1) & 1);
+                mbar_expect_tx(&full[s], kTileBytes);
+                const int row = (tile_begin + i) * kBN;
+                tma_load_2d(sB + s * kTileBytes, &map_i, &full[s], 0, row);
+                tma_load_2d(sB + s * kTileBytes + kChunkBytes, &map_i, &full[s], 32, row);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            mbar_wait(afull, 0);
+            for (int i = 0; i < n_local; ++i) {
+                const int s = i % kStages, a = i % kAcc;
+                if (i >= kAcc) mbar_wait(&tempty[a], ((i / kAcc) - 1) & 1);
+                mbar_wait(&full[s], (i / kStages) & 1);
+                tc_fence_after();
+                const uint32_t b0 = smem_u32(sB + s * kTileBytes);
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const uint32_t a0 = smem_u32(sA + t * 2 * kChunkBytes);
+                    const uint32_t dcol = tmem_base + a * 256 + t * 128;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t off = (k >> 2) * kChunkBytes + (k & 3) * 32;
+                        umma_tf32(dcol, smem_desc_sw128(a0 + off), smem_desc_sw128(b0 + off), kIdesc, k > 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty[s]);
+                umma_commit(&tfull[a]);
+            }
+        }
+    } else if (warp == 2) {
+        // ===== mask producer: lane owns queries lane + 32*j, j = 0..7 =====
+        int cur[8], endp[8], nxt[8];
+        const int64_t gid_first = p.item_gids ? 0 : p.item_id_base + (int64_t)tile_begin * kBN;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t q = (int64_t)utile * kBM + lane + 32 * j;
+            cur[j] = 0; endp[j] = 0; nxt[j] = 0x7fffffff;
+            if (p.mask_rowptr && q < p.n_q && n_local > 0) {
+                const int64_t lo = p.mask_rowptr[q], hi = p.mask_rowptr[q + 1];
+                // first train item at or after the first global id of this split
+                const int first_gid = p.item_gids ? __ldg(p.item_gids + (int64_t)tile_begin * kBN) : (int)gid_first;
+                int64_t a = lo, b = hi;
+                while (a < b) {
+                    const int64_t mid = (a + b) >> 1;
+                    if (__ldg(p.mask_col + mid) < first_gid) a = mid + 1; else b = mid;
+                }
+                cur[j] = (int)(a - lo); endp[j] = (int)(hi - lo);
+                if (cur[j] < endp[j]) nxt[j] = __ldg(p.mask_col + a);
+            }
+        }
+        for (int i = 0; i < n_local; ++i) {
+            const int a = i % kAcc;
+            if (i >= kAcc) mbar_wait(&tempty[a], ((i / kAcc) - 1) & 1);
+            uint32_t* mk = sMask + a * 4 * kBM;
+            for (int w = lane; w < kBM; w += 32) {   // zero: [4][256] words, 4 KB
+                mk[w] = 0; mk[kBM + w] = 0; mk[2 * kBM + w] = 0; mk[3 * kBM + w] = 0;
+            }
+            const int64_t pos0 = (int64_t)(tile_begin + i) * kBN;
+            // bits common to every query: flagged items and positions past the end of the table
+            int gid_lo = 0, gid_hi = 0;   // global id range covered by this tile: [gid_lo, gid_hi]
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int64_t pos = pos0 + c * 32 + lane;
+                bool bad = pos >= p.n_items;
+                int gid = 0x7fffffff;
+                if (!bad) {
+                    gid = p.item_gids ? __ldg(p.item_gids + pos) : (int)(p.item_id_base + pos);
+                    if (p.item_flags) bad = (__ldg(p.item_flags + gid) & p.flag_exclude) != 0;
+                }
+                const unsigned bits = __ballot_sync(CR_FULL_MASK, bad);
+                if (lane == 0) sCommon[a * 4 + c] = bits;
+                if (c == 0) gid_lo = __shfl_sync(CR_FULL_MASK, gid, 0);
+                // last valid gid of the tile
+                const unsigned valid = __ballot_sync(CR_FULL_MASK, pos < p.n_items);
+                if (valid) gid_hi = __shfl_sync(CR_FULL_MASK, gid, 31 - __clz(valid));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                while (nxt[j] <= gid_hi) {
+                    int pos = -1;
+                    if (!p.item_gids) {
+                        pos = nxt[j] - gid_lo;
+                    } else if (nxt[j] >= gid_lo) {   // locate the id inside this tile of the compacted table
+                        int lo2 = 0, hi2 = (int)min((int64_t)kBN, p.n_items - pos0);
+                        while (lo2 < hi2) {
+                            const int mid = (lo2 + hi2) >> 1;
+                            if (__ldg(p.item_gids + pos0 + mid) < nxt[j]) lo2 = mid + 1; else hi2 = mid;
+                        }
+                        if (pos0 + lo2 < p.n_items && __ldg(p.item_gids + pos0 + lo2) == nxt[j]) pos = lo2;
+                    }
+                    if (pos >= 0 && pos < kBN) mk[(pos >> 5) * kBM + lane + 32 * j] |= 1u << (pos & 31);
+                    ++cur[j];
+                    const int64_t q = (int64_t)utile * kBM + lane + 32 * j;
+                    nxt[j] = (cur[j] < endp[j]) ? __ldg(p.mask_col + p.mask_rowptr[q] + cur[j]) : 0x7fffffff;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&mfull[a]);
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ===== epilogue: thread = one query = one TMEM lane =====
+        const int e = warp - kEpiWarp0;
+        const int t = e >> 2, quad = warp & 3;
+        const int ulocal = t * 128 + quad * 32 + lane;               // query index inside the unit
+        const int64_t q = (int64_t)utile * kBM + ulocal;
+        const bool valid = q < p.n_q;
+        float thr = valid ? -CUDART_INF_F : CUDART_INF_F;
+        int cnt = 0;
+        Cand* mybuf = p.buf + ((int64_t)split * p.n_q_pad + utile * kBM + ulocal) * CAP;
+        float* scratch = sScratch + e * 32;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+
+        for (int i = 0; i < n_local; ++i) {
+            const int a = i % kAcc;
+            mbar_wait(&tfull[a], (i / kAcc) & 1);
+            mbar_wait(&mfull[a], (i / kAcc) & 1);
+            tc_fence_after();
+            const int64_t pos0 = (int64_t)(tile_begin + i) * kBN;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                float v[32];
+                tmem_ld32(tmem_base + lane_addr + a * 256 + t * 128 + c * 32, v);
+                if (p.dbg_scores && blockIdx.x == 0 && i == 0) {
+#pragma unroll
+                    for (int x = 0; x < 32; ++x) p.dbg_scores[ulocal * kBN + c * 32 + x] = v[x];
+                }
+                float m = max3(v[0], v[1], v[2]);
+#pragma unroll
+                for (int x = 3; x < 31; x += 2) m = max3(m, v[x], v[x + 1]);
+                m = fmaxf(m, v[31]);
+                unsigned ev = __ballot_sync(CR_FULL_MASK, m > thr);
+                while (ev) {
+                    const int L = __ffs(ev) - 1;
+                    ev &= ev - 1;
+                    if (lane == L) {
+                        float4* dst = reinterpret_cast<float4*>(scratch);
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) dst[x] = make_float4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+                    }
+                    __syncwarp();
+                    const float x = scratch[lane];
+                    float thrL = __shfl_sync(CR_FULL_MASK, thr, L);
+                    int cntL = __shfl_sync(CR_FULL_MASK, cnt, L);
+                    const int uL = t * 128 + quad * 32 + L;
+                    const uint32_t bad = sMask[a * 4 * kBM + c * kBM + uL] | sCommon[a * 4 + c];
+                    const bool ok = !((bad >> lane) & 1u);
+                    bool pass = ok && x > thrL;
+                    unsigned pm = __ballot_sync(CR_FULL_MASK, pass);
+                    Cand* bufL = mybuf + (int64_t)(L - lane) * CAP;
+                    if (cntL + __popc(pm) > CAP) {
+                        thrL = warp_shrink<EPL>(bufL, cntL, KSEL, lane);
+                        cntL = KSEL;
+                        pass = ok && x > thrL;
+                        pm = __ballot_sync(CR_FULL_MASK, pass);
+                    }
+                    if (pass) {
+                        const int slot = cntL + __popc(pm & ((1u << lane) - 1u));
+                        reinterpret_cast<float2*>(bufL)[slot] = make_float2(x, __int_as_float((int)(pos0 + c * 32 + lane)));
+                    }
+                    if (lane == L) {
+                        cnt = cntL + __popc(pm);
+                        thr = thrL;
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[a]);
+        }
+        const int64_t o = (int64_t)split * p.n_q_pad + utile * kBM + ulocal;
+        p.cnt[o] = valid ? cnt : 0;
+        p.thr[o] = thr;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 3) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------- rescore
+struct RescoreParams {
+    const float* Q;              // [n_q_pad, 64] gathered queries
+    const float* item_tab;
+    const int32_t* item_gids; int64_t item_id_base;
+    int64_t n_q; int n_q_pad; int n_splits; int K; int cap; int ksel;
+    const Cand* buf; const int* cnt; const float* thr;
+    const float* item_norm2_max;  // device scalar: max_i |x_i|^2
+    float* part_score; int32_t* part_id;   // [S][n_q][K]
+    int32_t* refine_flag;        // [n_q] 0/1
+    int32_t* refine_list; int32_t* refine_count;
+};
+
+// One warp per (query, split): exact fp32 scores of the candidates, top-K by (score desc, gid asc),
+// margin proof.  Candidates are never masked items (the sweep's bitmap dropped those).
+template <int EPL>
+__global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= p.n_q * p.n_splits) return;
+    const int split = (int)(w / p.n_q);
+    const int64_t q = w % p.n_q;
+    const int64_t o = (int64_t)split * p.n_q_pad + q;
+    const int cnt = min(p.cnt[o], p.cap);
+    const float thr = p.thr[o];
+    const Cand* buf = p.buf + o * p.cap;
+    const float4* qv = reinterpret_cast<const float4*>(p.Q + q * kD);
+
+    float es[EPL];
+    int eg[EPL];
+    float qn2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kD / 4; ++k) {
+        const float4 a = __ldg(qv + k);
+        qn2 = fmaf(a.x, a.x, qn2); qn2 = fmaf(a.y, a.y, qn2); qn2 = fmaf(a.z, a.z, qn2); qn2 = fmaf(a.w, a.w, qn2);
+    }
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        const int idx = lane + 32 * i;
+        es[i] = -CUDART_INF_F;
+        eg[i] = 0x7fffffff;
+        if (idx < cnt) {
+            const int pos = buf[idx].p;
+            const float4* xv = reinterpret_cast<const float4*>(p.item_tab + (int64_t)pos * kD);
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < kD / 4; ++k) {
+                const float4 a = __ldg(qv + k), b = __ldg(xv + k);
+                s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+            }
+            es[i] = s;
+            eg[i] = p.item_gids ? __ldg(p.item_gids + pos) : (int)(p.item_id_base + pos);
+        }
+    }
+    int rank[EPL];
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) rank[i] = 0;
+    for (int j = 0; j < 32; ++j) {
+#pragma unroll
+        for (int i2 = 0; i2 < EPL; ++i2) {
+            const float s = __shfl_sync(CR_FULL_MASK, es[i2], j);
+            const int g = __shfl_sync(CR_FULL_MASK, eg[i2], j);
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) rank[i] += cr::better(s, g, es[i], eg[i]) ? 1 : 0;
+        }
+    }
+    const int K = p.K;
+    float* os = p.part_score + ((int64_t)split * p.n_q + q) * K;
+    int32_t* oi = p.part_id + ((int64_t)split * p.n_q + q) * K;
+    for (int k = cnt + lane; k < K; k += 32) { os[k] = -CUDART_INF_F; oi[k] = -1; }
+    float kth = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        const bool have = lane + 32 * i < cnt;
+        if (have && rank[i] < K) { os[rank[i]] = es[i]; oi[rank[i]] = eg[i]; }
+        const unsigned who = __ballot_sync(CR_FULL_MASK, have && rank[i] == K - 1);
+        if (who) kth = __shfl_sync(CR_FULL_MASK, es[i], __ffs(who) - 1);
+    }
+    // proof: nothing was ever rejected by threshold (thr still -inf), or the K-th exact score clears thr + eps
+    bool proven = (thr == -CUDART_INF_F);
+    if (!proven && cnt >= K) {
+        const float eps = kEpsFactor * sqrtf(qn2) * sqrtf(*p.item_norm2_max);
+        proven = kth > thr + eps;
+    }
+    if (!proven && lane == 0) {
+        if (atomicExch(p.refine_flag + q, 1) == 0) p.refine_list[atomicAdd(p.refine_count, 1)] = (int32_t)q;
+    }
+}
+
+__global__ void item_norm_max_kernel(const float4* __restrict__ item4, int64_t n_items, float* out) {
+    float m = 0.f;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_items; r += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < kD / 4; ++k) {
+            const float4 a = __ldg(item4 + r * (kD / 4) + k);
+            s = fmaf(a.x, a.x, s); s = fmaf(a.y, a.y, s); s = fmaf(a.z, a.z, s); s = fmaf(a.w, a.w, s);
+        }
+        m = fmaxf(m, s);
+    }
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(CR_FULL_MASK, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));   // m >= 0: int order == float order
+}
+
+__global__ void gather_q_kernel(const float4* __restrict__ src, const int32_t* __restrict__ ids, int64_t n, float4* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * (kD / 4)) return;
+    const int64_t r = i / (kD / 4);
+    const int64_t row = ids ? (int64_t)__ldg(ids + r) : r;
+    dst[i] = __ldg(src + row * (kD / 4) + (i % (kD / 4)));
+}
+
+// Lists that came up short because masked items never become candidates here: append the first masked
+// items of the local table at CR_MASK_SCORE (the reference's top-K shows masked ids in that case).
+__global__ void fill_masked_local_kernel(float* __restrict__ out_score, int32_t* __restrict__ out_id, int64_t n_q, int K,
+                                         int64_t n_items, const int32_t* __restrict__ item_gids, int64_t item_id_base,
+                                         const uint8_t* __restrict__ item_flags, uint8_t flag_exclude,
+                                         const int64_t* __restrict__ mask_rowptr, const int32_t* __restrict__ mask_col) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_q) return;
+    float* os = out_score + q * K;
+    int32_t* oi = out_id + q * K;
+    int m = K;
+    while (m > 0 && oi[m - 1] < 0) --m;
+    if (m == K) return;
+    const int64_t lo = mask_rowptr ? mask_rowptr[q] : 0, hi = mask_rowptr ? mask_rowptr[q + 1] : 0;
+    for (int64_t pos = 0; pos < n_items && m < K; ++pos) {
+        const int gid = item_gids ? item_gids[pos] : (int)(item_id_base + pos);
+        bool masked = item_flags && (item_flags[gid] & flag_exclude);
+        if (!masked && mask_rowptr) masked = cr::csr_row_contains(mask_col, lo, hi, gid);
+        if (!masked) continue;
+        os[m] = CR_MASK_SCORE;
+        oi[m] = gid;
+        ++m;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+    static EncodeTiledFn cached = nullptr;
+    if (!cached) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess) return cr::note_cuda_error(e, "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)");
+        if (qres != cudaDriverEntryPointSuccess || !fn) return cr::note_cuda_error(cudaErrorUnknown, "cuTensorMapEncodeTiled lookup");
+        cached = (EncodeTiledFn)fn;
+    }
+    *out = cached;
+    return CR_OK;
+}
+
+// rows x 64 fp32, row-major; box = 32 floats x 128 rows, SWIZZLE_128B; out-of-range rows read as zero
+int make_map(CUtensorMap* map, const float* base, int64_t rows) {
+    EncodeTiledFn enc;
+    int rc = get_encode_fn(&enc);
+    if (rc != CR_OK) return rc;
+    cuuint64_t dims[2] = {(cuuint64_t)kD, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kD * sizeof(float)};
+    cuuint32_t box[2] = {32, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cr::note_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled");
+    return CR_OK;
+}
+
+struct TcPlan {
+    int ksel, cap, n_utiles, n_q_pad, n_tiles, S, tiles_per_split;
+    size_t off_q, off_buf, off_cnt, off_thr, off_norm, off_flag, off_list, off_count, off_ps, off_pi, off_exact, exact_bytes, total;
+};
+
+TcPlan tc_plan(int64_t n_q, int64_t n_items, int K) {
+    TcPlan P{};
+    P.ksel = (K <= 24) ? 32 : 64;
+    P.cap = P.ksel + 32;
+    P.n_utiles = (int)((n_q + kBM - 1) / kBM);
+    P.n_q_pad = P.n_utiles * kBM;
+    P.n_tiles = (int)((n_items + kBN - 1) / kBN);
+    // split the item range until there are ~8 waves of units, keeping >= 64 tiles per unit
+    int S = 1;
+    const int target = 148 * 8;
+    if (P.n_utiles > 0) S = (target + P.n_utiles - 1) / P.n_utiles;
+    const int max_by_tiles = (P.n_tiles + 63) / 64;
+    if (S > max_by_tiles) S = max_by_tiles;
+    if (S > 32) S = 32;
+    if (S < 1) S = 1;
+    P.tiles_per_split = (P.n_tiles + S - 1) / S;
+    if (P.tiles_per_split < 1) P.tiles_per_split = 1;
+    P.S = (P.n_tiles + P.tiles_per_split - 1) / P.tiles_per_split;
+    if (P.S < 1) P.S = 1;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = cr::align_up(off + bytes, 256); return o; };
+    P.off_q = take((size_t)P.n_q_pad * kD * 4);
+    P.off_buf = take((size_t)P.S * P.n_q_pad * P.cap * sizeof(Cand));
+    P.off_cnt = take((size_t)P.S * P.n_q_pad * 4);
+    P.off_thr = take((size_t)P.S * P.n_q_pad * 4);
+    P.off_norm = take(256);
+    P.off_flag = take((size_t)(n_q > 0 ? n_q : 1) * 4);
+    P.off_list = take((size_t)(n_q > 0 ? n_q : 1) * 4);
+    P.off_count = take(256);
+    P.off_ps = take((size_t)P.S * n_q * K * 4);
+    P.off_pi = take((size_t)P.S * n_q * K * 4);
+    P.exact_bytes = cr::refine_workspace_bytes(K);
+    P.off_exact = take(P.exact_bytes);
+    P.total = off;
+    return P;
+}
+
+}  // namespace
+
+namespace cr {
+
+size_t tc_workspace_bytes(int64_t n_q, int64_t n_items, int d, int K) {
+    if (d != kD || K > 52) return exact_workspace_bytes(n_q, n_items, K);
+    return tc_plan(n_q, n_items, K).total;
+}
+
+int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_bytes, cudaStream_t st, float* dbg_scores) {
+    if (n_refined) CR_CUDA_TRY(cudaMemsetAsync(n_refined, 0, sizeof(int32_t), st));
+    if (j.d != kD || j.K > 52 || j.n_items == 0) {
+        // exact fp32 everywhere: a stricter result than TF32-checked asks for, never a weaker one
+        return launch_exact_scorer(j, ws, ws_bytes, st);
+    }
+    const int64_t n_q = j.n_q, n_items = j.n_items;
+    const int K = j.K;
+    if (n_q == 0) return CR_OK;
+    const TcPlan P = tc_plan(n_q, n_items, K);
+    if (!ws || ws_bytes < P.total) return CR_ERR_WORKSPACE;
+    if (!aligned16(ws)) return CR_ERR_ALIGN;
+    char* base = (char*)ws;
+    float* Q = (float*)(base + P.off_q);
+    Cand* buf = (Cand*)(base + P.off_buf);
+    int* cnt = (int*)(base + P.off_cnt);
+    float* thr = (float*)(base + P.off_thr);
+    float* norm = (float*)(base + P.off_norm);
+    int32_t* rflag = (int32_t*)(base + P.off_flag);
+    int32_t* rlist = (int32_t*)(base + P.off_list);
+    int32_t* rcount = (int32_t*)(base + P.off_count);
+    float* part_s = (P.S > 1) ? (float*)(base + P.off_ps) : j.out_score;
+    int32_t* part_i = (P.S > 1) ? (int32_t*)(base + P.off_pi) : j.out_id;
+    const uint8_t* flags = j.flag_exclude ? j.item_flags : nullptr;
+
+    CR_CUDA_TRY(cudaMemsetAsync(norm, 0, 256, st));
+    CR_CUDA_TRY(cudaMemsetAsync(rflag, 0, (size_t)n_q * 4, st));
+    CR_CUDA_TRY(cudaMemsetAsync(rcount, 0, 256, st));
+    {
+        const int64_t total = n_q * (kD / 4);
+        gather_q_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float4*)j.user_tab, j.user_ids, n_q, (float4*)Q);
+        CR_LAUNCH_CHECK("gather_q_kernel");
+        item_norm_max_kernel<<<148 * 4, 256, 0, st>>>((const float4*)j.item_tab, n_items, norm);
+        CR_LAUNCH_CHECK("item_norm_max_kernel");
+    }
+    CUtensorMap map_q, map_i;
+    int rc = make_map(&map_q, Q, n_q);
+    if (rc != CR_OK) return rc;
+    rc = make_map(&map_i, j.item_tab, n_items);
+    if (rc != CR_OK) return rc;
+
+    SweepParams sp{};
+    sp.n_q = n_q; sp.n_q_pad = P.n_q_pad; sp.n_utiles = P.n_utiles; sp.n_items = n_items;
+    sp.tiles_per_split = P.tiles_per_split; sp.n_tiles = P.n_tiles; sp.item_gids = j.item_gids; sp.item_id_base = j.item_id_base;
+    sp.mask_rowptr = j.mask_rowptr; sp.mask_col = j.mask_col; sp.item_flags = flags;
+    sp.flag_exclude = j.flag_exclude; sp.buf = buf; sp.cnt = cnt; sp.thr = thr; sp.dbg_scores = dbg_scores;
+    const unsigned grid = (unsigned)(P.n_utiles * P.S);
+    if (P.ksel == 32) {
+        CR_CUDA_TRY(cudaFuncSetAttribute(score_sweep_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::kTotal));
+        score_sweep_tc_kernel<32><<<grid, kThreads, SmemLayout::kTotal, st>>>(map_q, map_i, sp);
+    } else {
+        CR_CUDA_TRY(cudaFuncSetAttribute(score_sweep_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::kTotal));
+        score_sweep_tc_kernel<64><<<grid, kThreads, SmemLayout::kTotal, st>>>(map_q, map_i, sp);
+    }
+    CR_LAUNCH_CHECK("score_sweep_tc_kernel");
+
+    RescoreParams rp{Q, j.item_tab, j.item_gids, j.item_id_base, n_q, P.n_q_pad, P.S, K, P.cap, P.ksel, buf, cnt, thr, norm,
+                     part_s, part_i, rflag, rlist, rcount};
+    const int64_t warps = n_q * P.S;
+    const unsigned rgrid = (unsigned)((warps * 32 + 255) / 256);
+    if (P.cap == 64) rescore_kernel<2><<<rgrid, 256, 0, st>>>(rp); else rescore_kernel<3><<<rgrid, 256, 0, st>>>(rp);
+    CR_LAUNCH_CHECK("rescore_kernel");
+    if (P.S > 1) {
+        rc = launch_merge(part_s, part_i, P.S, n_q, K, j.out_score, j.out_id, st, nullptr, 0, 0, -1, INT64_MAX);
+        if (rc != CR_OK) return rc;
+    }
+    // lists shorter than K (fewer than K unmasked items): show masked ids at -1e9 like the reference's top-K
+    if (j.mask_rowptr || flags) {
+        fill_masked_local_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, st>>>(j.out_score, j.out_id, n_q, K, n_items, j.item_gids,
+                                                                               j.item_id_base, flags, j.flag_exclude,
+                                                                               j.mask_rowptr, j.mask_col);
+        CR_LAUNCH_CHECK("fill_masked_local_kernel");
+    }
+    // queries whose margin could not be proven: exact fp32 re-run, rows overwritten in place
+    ExactJob ej = j;
+    ej.item_flags = flags;
+    rc = launch_exact_refine(ej, RefineList{rlist, rcount, n_q}, base + P.off_exact, P.exact_bytes, st);
+    if (rc != CR_OK) return rc;
+    if (n_refined) CR_CUDA_TRY(cudaMemcpyAsync(n_refined, rcount, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return CR_OK;
+}
+
+}  // namespace cr

@@ -1,0 +1,324 @@
+// K3 — warp-per-row CSR SpMM with 128-bit embedding gathers and a fused layer-mean epilogue.
+//
+// Replaces torch.sparse.mm(norm_adj, E) (model/LightGCN.py:90 and the other call sites listed in
+// include/coldrec_b200.h) plus the stack/mean of LightGCN.py:92-93.  HBM-bound: per nonzero one
+// 4-byte column id, one 4-byte value and one d*4-byte row gather; per row one write of y and an
+// optional read-modify-write of the running layer sum.
+//
+// Layout: a row of d floats is covered by LPR lanes holding NV float4 each (d = 4*LPR*NV); the
+// 32/LPR lane groups of a warp walk different nonzeros of the same row, U nonzeros each in flight,
+// so a warp keeps U*(32/LPR) row gathers (2 KB at d=64) outstanding.  Rows longer than kLongRow are
+// cut into kChunk-nonzero chunks (one warp each, partial sums in the plan buffer) and reduced in
+// chunk order by a third kernel, so results do not depend on scheduling.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kLongRow = 512;
+constexpr int kChunk = 512;
+constexpr int kThreads = 256;
+
+struct PlanHeader {
+    int n_chunks;
+    int n_long;
+    int overflow;
+    int pad;
+};
+struct LongRow {
+    int row;
+    int chunk_base;
+    int n_chunks;
+    int pad;
+};
+struct Chunk {
+    int64_t start;
+    int len;
+    int row;
+};
+
+struct PlanLayout {
+    int64_t max_long, max_chunks;
+    size_t off_long, off_chunks, off_partial, total;
+};
+
+PlanLayout plan_layout(int64_t nnz, int d) {
+    PlanLayout L;
+    L.max_long = nnz / (kLongRow + 1) + 1;
+    L.max_chunks = nnz / kChunk + L.max_long + 1;
+    L.off_long = 256;
+    L.off_chunks = cr::align_up(L.off_long + (size_t)L.max_long * sizeof(LongRow), 256);
+    L.off_partial = cr::align_up(L.off_chunks + (size_t)L.max_chunks * sizeof(Chunk), 256);
+    L.total = cr::align_up(L.off_partial + (size_t)L.max_chunks * d * sizeof(float), 256);
+    return L;
+}
+
+__device__ __forceinline__ void fma4(float4& a, float w, const float4& x) {
+    a.x = fmaf(w, x.x, a.x);
+    a.y = fmaf(w, x.y, a.y);
+    a.z = fmaf(w, x.z, a.z);
+    a.w = fmaf(w, x.w, a.w);
+}
+
+// Accumulate nonzeros [s, e) of one row into per-lane-group partial sums a[].
+template <int LPR, int NV, bool HAS_VAL, bool BOUNDS>
+__device__ __forceinline__ void accumulate_range(const int32_t* __restrict__ col, const float* __restrict__ val,
+                                                 int64_t s, int64_t e, const float4* __restrict__ X4, int d4, int lane,
+                                                 float4 (&a)[NV]) {
+    constexpr int G = 32 / LPR;
+    constexpr int U = 4;
+    const int grp = lane / LPR, sub = lane % LPR;
+    for (int64_t base = s; base < e; base += 32) {
+        const int64_t j = base + lane;
+        int c = 0;
+        float v = 0.f;
+        if (j < e) {
+            c = __ldg(col + j);
+            v = HAS_VAL ? __ldg(val + j) : 1.f;
+        }
+        const int cnt = (int)min((int64_t)32, e - base);
+        for (int t = 0; t < cnt; t += G * U) {
+            float4 x[U][NV];
+            float w[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int src = t + u * G + grp;
+                const int cc = __shfl_sync(CR_FULL_MASK, c, src & 31);
+                const float ww = __shfl_sync(CR_FULL_MASK, v, src & 31);
+                const bool ok = src < cnt;
+                w[u] = ok ? ww : 0.f;
+                const float4* p = X4 + (int64_t)cc * d4 + sub;
+#pragma unroll
+                for (int nv = 0; nv < NV; ++nv) {
+                    const bool okc = ok && (!BOUNDS || sub + nv * LPR < d4);
+                    x[u][nv] = okc ? __ldg(p + nv * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int nv = 0; nv < NV; ++nv) fma4(a[nv], w[u], x[u][nv]);
+        }
+    }
+}
+
+template <int LPR, int NV>
+__device__ __forceinline__ void reduce_groups(float4 (&a)[NV]) {
+#pragma unroll
+    for (int off = LPR; off < 32; off <<= 1)
+#pragma unroll
+        for (int nv = 0; nv < NV; ++nv) {
+            a[nv].x += __shfl_xor_sync(CR_FULL_MASK, a[nv].x, off);
+            a[nv].y += __shfl_xor_sync(CR_FULL_MASK, a[nv].y, off);
+            a[nv].z += __shfl_xor_sync(CR_FULL_MASK, a[nv].z, off);
+            a[nv].w += __shfl_xor_sync(CR_FULL_MASK, a[nv].w, off);
+        }
+}
+
+// y -> Y and/or acc = (beta*acc_in + y) / div for one float4 of one row (acc_in may alias acc).
+__device__ __forceinline__ void store_epilogue(float4* __restrict__ Y4, const float4* acc_in4, float4* acc4, int64_t idx,
+                                               float4 y, float beta, float div) {
+    if (Y4) Y4[idx] = y;
+    if (acc4) {
+        float4 o = y;
+        if (beta != 0.f) {
+            const float4 p = acc_in4[idx];
+            o.x = fmaf(beta, p.x, y.x);
+            o.y = fmaf(beta, p.y, y.y);
+            o.z = fmaf(beta, p.z, y.z);
+            o.w = fmaf(beta, p.w, y.w);
+        }
+        if (div != 1.f) {
+            o.x = __fdiv_rn(o.x, div);
+            o.y = __fdiv_rn(o.y, div);
+            o.z = __fdiv_rn(o.z, div);
+            o.w = __fdiv_rn(o.w, div);
+        }
+        acc4[idx] = o;
+    }
+}
+
+template <int LPR, int NV, bool HAS_VAL, bool BOUNDS>
+__global__ void __launch_bounds__(kThreads)
+spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+                 int64_t n_rows, const float4* __restrict__ X4, int d4, float4* __restrict__ Y4,
+                 const float4* acc_in4, float4* acc4, float beta, float div, int long_row) {
+    const int64_t row = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t s = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+    if (e - s > long_row) return;   // split path owns this row
+    float4 a[NV];
+#pragma unroll
+    for (int nv = 0; nv < NV; ++nv) a[nv] = make_float4(0.f, 0.f, 0.f, 0.f);
+    accumulate_range<LPR, NV, HAS_VAL, BOUNDS>(col, val, s, e, X4, d4, lane, a);
+    reduce_groups<LPR, NV>(a);
+    if (lane < LPR) {
+#pragma unroll
+        for (int nv = 0; nv < NV; ++nv)
+            if (!BOUNDS || lane + nv * LPR < d4) store_epilogue(Y4, acc_in4, acc4, row * d4 + lane + nv * LPR, a[nv], beta, div);
+    }
+}
+
+__global__ void spmm_plan_kernel(const int64_t* __restrict__ rowptr, int64_t n_rows, PlanHeader* hdr, LongRow* long_rows,
+                                 Chunk* chunks, int max_long, int max_chunks) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const int64_t s = rowptr[row], len = rowptr[row + 1] - s;
+    if (len <= kLongRow) return;
+    const int nch = (int)((len + kChunk - 1) / kChunk);
+    const int base = atomicAdd(&hdr->n_chunks, nch);
+    const int li = atomicAdd(&hdr->n_long, 1);
+    if (base + nch > max_chunks || li >= max_long) {   // unreachable with plan_layout()'s bounds
+        hdr->overflow = 1;
+        return;
+    }
+    long_rows[li] = LongRow{(int)row, base, nch, 0};
+    for (int c = 0; c < nch; ++c) {
+        const int64_t off = (int64_t)c * kChunk;
+        chunks[base + c] = Chunk{s + off, (int)min((int64_t)kChunk, len - off), (int)row};
+    }
+}
+
+template <int LPR, int NV, bool HAS_VAL, bool BOUNDS>
+__global__ void __launch_bounds__(kThreads)
+spmm_long_chunks_kernel(const PlanHeader* __restrict__ hdr, const Chunk* __restrict__ chunks,
+                        const int32_t* __restrict__ col, const float* __restrict__ val, const float4* __restrict__ X4,
+                        int d4, float4* __restrict__ partial4) {
+    const int lane = threadIdx.x & 31;
+    const int n_chunks = hdr->n_chunks;
+    const int warps = (gridDim.x * kThreads) >> 5;
+    for (int c = (blockIdx.x * kThreads + threadIdx.x) >> 5; c < n_chunks; c += warps) {
+        const Chunk ch = chunks[c];
+        float4 a[NV];
+#pragma unroll
+        for (int nv = 0; nv < NV; ++nv) a[nv] = make_float4(0.f, 0.f, 0.f, 0.f);
+        accumulate_range<LPR, NV, HAS_VAL, BOUNDS>(col, val, ch.start, ch.start + ch.len, X4, d4, lane, a);
+        reduce_groups<LPR, NV>(a);
+        if (lane < LPR) {
+#pragma unroll
+            for (int nv = 0; nv < NV; ++nv)
+                if (!BOUNDS || lane + nv * LPR < d4) partial4[(int64_t)c * d4 + lane + nv * LPR] = a[nv];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+spmm_long_reduce_kernel(const PlanHeader* __restrict__ hdr, const LongRow* __restrict__ long_rows,
+                        const float4* __restrict__ partial4, int d4, float4* __restrict__ Y4, const float4* acc_in4,
+                        float4* acc4, float beta, float div) {
+    const int lane = threadIdx.x & 31;
+    const int n_long = hdr->n_long;
+    const int warps = (gridDim.x * kThreads) >> 5;
+    for (int li = (blockIdx.x * kThreads + threadIdx.x) >> 5; li < n_long; li += warps) {
+        const LongRow lr = long_rows[li];
+        for (int i = lane; i < d4; i += 32) {
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c = 0; c < lr.n_chunks; ++c) {     // fixed chunk order: deterministic
+                const float4 p = partial4[(int64_t)(lr.chunk_base + c) * d4 + i];
+                sum.x += p.x; sum.y += p.y; sum.z += p.z; sum.w += p.w;
+            }
+            store_epilogue(Y4, acc_in4, acc4, (int64_t)lr.row * d4 + i, sum, beta, div);
+        }
+    }
+}
+
+struct SpmmArgs {
+    const int64_t* rowptr; const int32_t* col; const float* val; int64_t n_rows; const float4* X4; int d4;
+    float4* Y4; const float4* acc_in4; float4* acc4; float beta, div;
+    PlanHeader* hdr; LongRow* long_rows; Chunk* chunks; float4* partial4;
+    cudaStream_t stream;
+};
+
+template <int LPR, int NV, bool BOUNDS>
+int launch_spmm(const SpmmArgs& a) {
+    const int long_row = a.hdr ? kLongRow : 0x7fffffff;
+    const int64_t blocks = (a.n_rows * 32 + kThreads - 1) / kThreads;
+    if (blocks > 0x7fffffffLL) return CR_ERR_UNSUPPORTED;
+    if (a.n_rows > 0) {
+        if (a.val)
+            spmm_rows_kernel<LPR, NV, true, BOUNDS><<<(unsigned)blocks, kThreads, 0, a.stream>>>(
+                a.rowptr, a.col, a.val, a.n_rows, a.X4, a.d4, a.Y4, a.acc_in4, a.acc4, a.beta, a.div, long_row);
+        else
+            spmm_rows_kernel<LPR, NV, false, BOUNDS><<<(unsigned)blocks, kThreads, 0, a.stream>>>(
+                a.rowptr, a.col, a.val, a.n_rows, a.X4, a.d4, a.Y4, a.acc_in4, a.acc4, a.beta, a.div, long_row);
+        CR_LAUNCH_CHECK("spmm_rows_kernel");
+    }
+    if (a.hdr) {
+        const int grid = 148 * 8;
+        if (a.val)
+            spmm_long_chunks_kernel<LPR, NV, true, BOUNDS><<<grid, kThreads, 0, a.stream>>>(a.hdr, a.chunks, a.col, a.val,
+                                                                                            a.X4, a.d4, a.partial4);
+        else
+            spmm_long_chunks_kernel<LPR, NV, false, BOUNDS><<<grid, kThreads, 0, a.stream>>>(a.hdr, a.chunks, a.col, a.val,
+                                                                                             a.X4, a.d4, a.partial4);
+        CR_LAUNCH_CHECK("spmm_long_chunks_kernel");
+        spmm_long_reduce_kernel<<<148, kThreads, 0, a.stream>>>(a.hdr, a.long_rows, a.partial4, a.d4, a.Y4, a.acc_in4, a.acc4,
+                                                                a.beta, a.div);
+        CR_LAUNCH_CHECK("spmm_long_reduce_kernel");
+    }
+    return CR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t cr_spmm_plan_bytes(int64_t n_rows, int64_t nnz, int d) {
+    (void)n_rows;
+    if (nnz < 0 || d <= 0) return 0;
+    return plan_layout(nnz, d).total;
+}
+
+int cr_spmm_plan(const int64_t* rowptr, int64_t n_rows, int64_t nnz, int d, void* plan, size_t plan_bytes, void* stream) {
+    if (!rowptr || !plan || n_rows < 0 || nnz < 0 || d <= 0) return CR_ERR_ARG;
+    if (n_rows > 0x7fffffffLL) return CR_ERR_UNSUPPORTED;
+    const PlanLayout L = plan_layout(nnz, d);
+    if (plan_bytes < L.total) return CR_ERR_WORKSPACE;
+    if (L.max_chunks > 0x7fffffffLL) return CR_ERR_UNSUPPORTED;
+    int rc = cr::require_device();
+    if (rc != CR_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = (char*)plan;
+    CR_CUDA_TRY(cudaMemsetAsync(base, 0, 256, st));
+    if (n_rows > 0) {
+        const unsigned blocks = (unsigned)((n_rows + 255) / 256);
+        spmm_plan_kernel<<<blocks, 256, 0, st>>>(rowptr, n_rows, (PlanHeader*)base, (LongRow*)(base + L.off_long),
+                                                 (Chunk*)(base + L.off_chunks), (int)L.max_long, (int)L.max_chunks);
+        CR_LAUNCH_CHECK("spmm_plan_kernel");
+    }
+    return CR_OK;
+}
+
+int cr_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, int64_t nnz,
+                    const float* X, int d, float* Y, const float* acc_in, float* acc, float acc_beta, float acc_div,
+                    void* plan, size_t plan_bytes, void* stream) {
+    if (!rowptr || (!col && nnz > 0) || !X || n_rows < 0 || nnz < 0 || (!Y && !acc) || acc_div == 0.f) return CR_ERR_ARG;
+    if (d <= 0 || d % 4 != 0 || d > 512) return CR_ERR_UNSUPPORTED;
+    if (!cr::aligned16(X) || !cr::aligned16(Y) || !cr::aligned16(acc) || !cr::aligned16(acc_in)) return CR_ERR_ALIGN;
+    if (acc_in && !acc) return CR_ERR_ARG;
+    int rc = cr::require_device();
+    if (rc != CR_OK) return rc;
+    SpmmArgs a{rowptr, col, val, n_rows, (const float4*)X, d / 4, (float4*)Y, (const float4*)(acc_in ? acc_in : acc), (float4*)acc, acc_beta, acc_div,
+               nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream};
+    if (plan) {
+        const PlanLayout L = plan_layout(nnz, d);
+        if (plan_bytes < L.total) return CR_ERR_WORKSPACE;
+        char* base = (char*)plan;
+        a.hdr = (PlanHeader*)base;
+        a.long_rows = (LongRow*)(base + L.off_long);
+        a.chunks = (Chunk*)(base + L.off_chunks);
+        a.partial4 = (float4*)(base + L.off_partial);
+    }
+    switch (d) {
+        case 32: return launch_spmm<8, 1, false>(a);
+        case 64: return launch_spmm<16, 1, false>(a);
+        case 128: return launch_spmm<32, 1, false>(a);
+        case 256: return launch_spmm<32, 2, false>(a);
+        default:
+            if (d <= 128) return launch_spmm<32, 1, true>(a);
+            if (d <= 256) return launch_spmm<32, 2, true>(a);
+            return launch_spmm<32, 4, true>(a);
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,298 @@
+"""Tensor-level wrappers over the C ABI.  PyTorch is used only for device memory and streams.
+
+Every function validates device / dtype / contiguity and raises instead of casting silently, then
+passes raw device pointers and the current CUDA stream to ``libcoldrec_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+__all__ = ["spmm_plan", "spmm", "score_topk", "topk_merge", "fill_masked", "gather_rows", "rank_metrics", "linear_act", "bn_fold",
+           "heater_blend", "SCORE_EXACT_F32", "SCORE_TF32_CHECKED"]
+
+SCORE_EXACT_F32 = _lib.SCORE_EXACT_F32
+SCORE_TF32_CHECKED = _lib.SCORE_TF32_CHECKED
+_ACTS = {None: _lib.ACT_NONE, "none": _lib.ACT_NONE, "tanh": _lib.ACT_TANH, "leaky_relu": _lib.ACT_LEAKY_RELU}
+
+
+def _req(t: Optional[torch.Tensor], dtype, name: str, optional=False, contiguous=True):
+    if t is None:
+        if optional:
+            return None
+        raise ValueError(f"{name} is required")
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (coldrec_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype} (no silent casts)")
+    if contiguous and not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(dev) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _same_device(*ts):
+    devs = {t.device for t in ts if t is not None}
+    if len(devs) > 1:
+        raise ValueError(f"tensors live on different devices: {devs}")
+    return next(iter(devs))
+
+
+# ------------------------------------------------------------------------------------------------ K3
+def spmm_plan(rowptr: torch.Tensor, nnz: int, d: int) -> torch.Tensor:
+    """Build the long-row split plan for one (rowptr, nnz, d); returns the opaque device buffer."""
+    lib = _lib.load()
+    rowptr = _req(rowptr, torch.int64, "rowptr")
+    n_rows = rowptr.numel() - 1
+    nbytes = lib.cr_spmm_plan_bytes(n_rows, nnz, d)
+    plan = torch.empty(nbytes, dtype=torch.uint8, device=rowptr.device)
+    with torch.cuda.device(rowptr.device):
+        _lib.check(lib.cr_spmm_plan(_ptr(rowptr), n_rows, nnz, d, _ptr(plan), nbytes, _stream(rowptr.device)), "cr_spmm_plan")
+    return plan
+
+
+def spmm(rowptr, col, val, X, Y=None, acc=None, acc_beta: float = 1.0, acc_div: float = 1.0, plan=None, acc_in=None):
+    """y = A.X over the local row block; Y = y and/or acc = (acc_beta*acc + y)/acc_div (see the header)."""
+    lib = _lib.load()
+    rowptr = _req(rowptr, torch.int64, "rowptr")
+    col = _req(col, torch.int32, "col")
+    val = _req(val, torch.float32, "val", optional=True)
+    X = _req(X, torch.float32, "X")
+    Y = _req(Y, torch.float32, "Y", optional=True)
+    acc = _req(acc, torch.float32, "acc", optional=True)
+    acc_in = _req(acc_in, torch.float32, "acc_in", optional=True)
+    dev = _same_device(rowptr, col, val, X, Y, acc, acc_in, plan)
+    n_rows, nnz, d = rowptr.numel() - 1, col.numel(), X.shape[1]
+    if val is not None and val.numel() != nnz:
+        raise ValueError("val and col differ in length")
+    for t, name in ((Y, "Y"), (acc, "acc"), (acc_in, "acc_in")):
+        if t is not None and tuple(t.shape) != (n_rows, d):
+            raise ValueError(f"{name} must be ({n_rows}, {d}), got {tuple(t.shape)}")
+    with torch.cuda.device(dev):
+        rc = lib.cr_spmm_csr_f32(_ptr(rowptr), _ptr(col), _ptr(val), n_rows, nnz, _ptr(X), d, _ptr(Y), _ptr(acc_in), _ptr(acc),
+                                 float(acc_beta), float(acc_div), _ptr(plan), 0 if plan is None else plan.numel(), _stream(dev))
+    _lib.check(rc, "cr_spmm_csr_f32")
+    return Y if Y is not None else acc
+
+
+# ------------------------------------------------------------------------------------------------ K1
+def score_topk(user_tab, item_tab, K: int, *, user_ids=None, item_gids=None, item_id_base: int = 0, mask_rowptr=None,
+               mask_col=None, item_flags=None, flag_exclude: int = 0, precision: int = SCORE_EXACT_F32,
+               out_score=None, out_id=None, workspace=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Fused score -> mask -> top-K.  Returns (scores [n_q,K] fp32, ids [n_q,K] int32, n_refined int32[1])."""
+    lib = _lib.load()
+    user_tab = _req(user_tab, torch.float32, "user_tab")
+    item_tab = _req(item_tab, torch.float32, "item_tab")
+    user_ids = _req(user_ids, torch.int32, "user_ids", optional=True)
+    item_gids = _req(item_gids, torch.int32, "item_gids", optional=True)
+    mask_rowptr = _req(mask_rowptr, torch.int64, "mask_rowptr", optional=True)
+    mask_col = _req(mask_col, torch.int32, "mask_col", optional=True)
+    item_flags = _req(item_flags, torch.uint8, "item_flags", optional=True)
+    dev = _same_device(user_tab, item_tab, user_ids, item_gids, mask_rowptr, mask_col, item_flags)
+    if user_tab.dim() != 2 or item_tab.dim() != 2 or user_tab.shape[1] != item_tab.shape[1]:
+        raise ValueError(f"user_tab {tuple(user_tab.shape)} and item_tab {tuple(item_tab.shape)} must share d")
+    d, n_items = item_tab.shape[1], item_tab.shape[0]
+    n_q = user_tab.shape[0] if user_ids is None else user_ids.numel()
+    if item_gids is not None and item_gids.numel() != n_items:
+        raise ValueError("item_gids must have one entry per item_tab row")
+    if mask_rowptr is not None and mask_rowptr.numel() != n_q + 1:
+        raise ValueError(f"mask_rowptr must have n_q+1={n_q + 1} entries")
+    if out_score is None:
+        out_score = torch.empty((n_q, K), dtype=torch.float32, device=dev)
+    if out_id is None:
+        out_id = torch.empty((n_q, K), dtype=torch.int32, device=dev)
+    _req(out_score, torch.float32, "out_score"); _req(out_id, torch.int32, "out_id")
+    n_ref = torch.zeros(1, dtype=torch.int32, device=dev)
+    need = lib.cr_score_topk_workspace_bytes(n_q, n_items, d, K, precision)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cr_score_topk_f32(_ptr(user_tab), _ptr(user_ids), n_q, _ptr(item_tab), _ptr(item_gids), item_id_base, n_items,
+                                   d, _ptr(mask_rowptr), _ptr(mask_col), _ptr(item_flags), flag_exclude, K, _ptr(out_score),
+                                   _ptr(out_id), _ptr(n_ref), precision, _ptr(workspace), workspace.numel(), _stream(dev))
+    _lib.check(rc, "cr_score_topk_f32")
+    return out_score, out_id, n_ref
+
+
+def debug_tc_tile(user_tab, item_tab, K: int = 20):
+    """Diagnostic: TF32-checked scoring (d=64, no masks) + raw tensor-core scores of the first 256x128 block."""
+    lib = _lib.load()
+    user_tab = _req(user_tab, torch.float32, "user_tab"); item_tab = _req(item_tab, torch.float32, "item_tab")
+    dev = _same_device(user_tab, item_tab)
+    n_q, n_items = user_tab.shape[0], item_tab.shape[0]
+    out_s = torch.empty((n_q, K), dtype=torch.float32, device=dev)
+    out_i = torch.empty((n_q, K), dtype=torch.int32, device=dev)
+    dbg = torch.zeros((256, 128), dtype=torch.float32, device=dev)
+    need = lib.cr_score_topk_workspace_bytes(n_q, n_items, 64, K, SCORE_TF32_CHECKED)
+    ws = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cr_debug_tc_tile(_ptr(user_tab), n_q, _ptr(item_tab), n_items, K, _ptr(out_s), _ptr(out_i), _ptr(dbg), _ptr(ws),
+                                  ws.numel(), _stream(dev))
+    _lib.check(rc, "cr_debug_tc_tile")
+    return out_s, out_i, dbg
+
+
+def topk_merge(in_score: torch.Tensor, in_id: torch.Tensor, out_score=None, out_id=None):
+    """Merge [G, n_q, K] candidate lists into [n_q, K] by (score desc, id asc)."""
+    lib = _lib.load()
+    in_score = _req(in_score, torch.float32, "in_score")
+    in_id = _req(in_id, torch.int32, "in_id")
+    if in_score.dim() != 3 or in_score.shape != in_id.shape:
+        raise ValueError("in_score/in_id must both be [G, n_q, K]")
+    dev = _same_device(in_score, in_id)
+    G, n_q, K = in_score.shape
+    if out_score is None:
+        out_score = torch.empty((n_q, K), dtype=torch.float32, device=dev)
+    if out_id is None:
+        out_id = torch.empty((n_q, K), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cr_topk_merge(_ptr(in_score), _ptr(in_id), G, n_q, K, _ptr(out_score), _ptr(out_id), _stream(dev))
+    _lib.check(rc, "cr_topk_merge")
+    return out_score, out_id
+
+
+def fill_masked(out_score, out_id, n_items_total: int, item_flags=None, flag_exclude: int = 0, mask_rowptr=None, mask_col=None):
+    """Complete short lists (trailing id -1) with masked ids at CR_MASK_SCORE, in place."""
+    lib = _lib.load()
+    _req(out_score, torch.float32, "out_score"); _req(out_id, torch.int32, "out_id")
+    item_flags = _req(item_flags, torch.uint8, "item_flags", optional=True)
+    mask_rowptr = _req(mask_rowptr, torch.int64, "mask_rowptr", optional=True)
+    mask_col = _req(mask_col, torch.int32, "mask_col", optional=True)
+    dev = _same_device(out_score, out_id, item_flags, mask_rowptr, mask_col)
+    n_q, K = out_id.shape
+    with torch.cuda.device(dev):
+        rc = lib.cr_fill_masked(_ptr(out_score), _ptr(out_id), n_q, K, n_items_total, _ptr(item_flags), flag_exclude,
+                                _ptr(mask_rowptr), _ptr(mask_col), _stream(dev))
+    _lib.check(rc, "cr_fill_masked")
+    return out_score, out_id
+
+
+def gather_rows(src: torch.Tensor, ids: torch.Tensor, out=None) -> torch.Tensor:
+    lib = _lib.load()
+    src = _req(src, torch.float32, "src")
+    ids = _req(ids, torch.int32, "ids")
+    dev = _same_device(src, ids)
+    n, d = ids.numel(), src.shape[1]
+    if out is None:
+        out = torch.empty((n, d), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.cr_gather_rows_f32(_ptr(src), _ptr(ids), n, d, _ptr(out), _stream(dev)), "cr_gather_rows_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ K2
+def dcg_tables(K: int):
+    """1/log(n+2,2) and its running sums, computed with the reference's own expression and addition
+    order (util/evaluator.py:104-109) so device-side DCG/IDCG match it bit for bit."""
+    inv = [1.0 / math.log(n + 2, 2) for n in range(K)]
+    pre, s = [0.0], 0
+    for v in inv:
+        s += v
+        pre.append(float(s))
+    return inv, pre
+
+
+def rank_metrics(topk_id: torch.Tensor, gt_rowptr: torch.Tensor, gt_col: torch.Tensor, Ns: Sequence[int],
+                 per_query: bool = False):
+    """Device reduction of Hit/Precision/Recall/NDCG partials.  Returns (sums [nN,6] fp64 on device,
+    hits [nN,n_q] int32 | None, dcg [nN,n_q] fp64 | None)."""
+    lib = _lib.load()
+    topk_id = _req(topk_id, torch.int32, "topk_id")
+    gt_rowptr = _req(gt_rowptr, torch.int64, "gt_rowptr")
+    gt_col = _req(gt_col, torch.int32, "gt_col")
+    dev = _same_device(topk_id, gt_rowptr, gt_col)
+    n_q, K = topk_id.shape
+    if gt_rowptr.numel() != n_q + 1:
+        raise ValueError("gt_rowptr must have n_q+1 entries")
+    nN = len(Ns)
+    inv, pre = dcg_tables(K)
+    tab = torch.tensor(inv + pre, dtype=torch.float64, device=dev)
+    sums = torch.empty((nN, 6), dtype=torch.float64, device=dev)
+    hits = torch.empty((nN, n_q), dtype=torch.int32, device=dev) if per_query else None
+    dcg = torch.empty((nN, n_q), dtype=torch.float64, device=dev) if per_query else None
+    ws = torch.empty(lib.cr_rank_metrics_workspace_bytes(n_q, nN), dtype=torch.uint8, device=dev)
+    ns_arr = (ctypes.c_int32 * nN)(*[int(n) for n in Ns])
+    with torch.cuda.device(dev):
+        rc = lib.cr_rank_metrics(_ptr(topk_id), n_q, K, _ptr(gt_rowptr), _ptr(gt_col), ns_arr, nN, _ptr(tab),
+                                 ctypes.c_void_p(tab.data_ptr() + 8 * K), _ptr(hits), _ptr(dcg), _ptr(sums), _ptr(ws),
+                                 ws.numel(), _stream(dev))
+    _lib.check(rc, "cr_rank_metrics")
+    return sums, hits, dcg
+
+
+# ------------------------------------------------------------------------------------------------ K4
+def linear_act(X1, W, bias=None, *, X2=None, xrow=None, scale=None, shift=None, act=None, out=None, yrow=None):
+    """out[yrow] = act(([X1|X2][xrow] . W^T + bias) * scale + shift); W in nn.Linear layout [n_out, d1+d2]."""
+    lib = _lib.load()
+    X1 = _req(X1, torch.float32, "X1", contiguous=False)
+    X2 = _req(X2, torch.float32, "X2", optional=True, contiguous=False)
+    W = _req(W, torch.float32, "W")
+    bias = _req(bias, torch.float32, "bias", optional=True)
+    scale = _req(scale, torch.float32, "scale", optional=True)
+    shift = _req(shift, torch.float32, "shift", optional=True)
+    xrow = _req(xrow, torch.int32, "xrow", optional=True)
+    yrow = _req(yrow, torch.int32, "yrow", optional=True)
+    dev = _same_device(X1, X2, W, bias, scale, shift, xrow, yrow, out)
+    for t, name in ((X1, "X1"), (X2, "X2")):
+        if t is not None and (t.dim() != 2 or t.stride(1) != 1):
+            raise ValueError(f"{name} must be 2-D with unit inner stride")
+    d1, d2 = X1.shape[1], (0 if X2 is None else X2.shape[1])
+    n_out = W.shape[0]
+    if W.shape[1] != d1 + d2:
+        raise ValueError(f"W is {tuple(W.shape)}, inputs give k={d1 + d2}")
+    n_rows = xrow.numel() if xrow is not None else X1.shape[0]
+    if out is None:
+        if yrow is not None:
+            raise ValueError("a scatter (yrow) needs an existing `out` table")
+        out = torch.empty((n_rows, n_out), dtype=torch.float32, device=dev)
+    _req(out, torch.float32, "out", contiguous=False)
+    if act not in _ACTS:
+        raise ValueError(f"unknown activation {act!r}")
+    with torch.cuda.device(dev):
+        rc = lib.cr_linear_act_f32(_ptr(X1), X1.stride(0), d1, _ptr(X2), 0 if X2 is None else X2.stride(0), d2, _ptr(xrow),
+                                   n_rows, _ptr(W), _ptr(bias), _ptr(scale), _ptr(shift), n_out, _ACTS[act], _ptr(out),
+                                   out.stride(0), _ptr(yrow), _stream(dev))
+    _lib.check(rc, "cr_linear_act_f32")
+    return out
+
+
+def bn_fold(gamma, beta, mean, var, eps: float):
+    """Eval-mode BatchNorm1d as (scale, shift)."""
+    lib = _lib.load()
+    mean = _req(mean, torch.float32, "running_mean"); var = _req(var, torch.float32, "running_var")
+    gamma = _req(gamma, torch.float32, "weight", optional=True); beta = _req(beta, torch.float32, "bias", optional=True)
+    dev = _same_device(mean, var, gamma, beta)
+    n = mean.numel()
+    scale = torch.empty(n, dtype=torch.float32, device=dev)
+    shift = torch.empty(n, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cr_bn_fold_f32(_ptr(gamma), _ptr(beta), _ptr(mean), _ptr(var), float(eps), n, _ptr(scale), _ptr(shift), _stream(dev))
+    _lib.check(rc, "cr_bn_fold_f32")
+    return scale, shift
+
+
+def heater_blend(gate, expert, Vin, keep: float, one_minus_keep: float):
+    lib = _lib.load()
+    gate = _req(gate, torch.float32, "gate"); expert = _req(expert, torch.float32, "expert"); Vin = _req(Vin, torch.float32, "Vin")
+    dev = _same_device(gate, expert, Vin)
+    n, d = expert.shape
+    if Vin.shape != expert.shape or gate.shape[0] != n:
+        raise ValueError("gate/expert/Vin row counts differ")
+    out = torch.empty_like(expert)
+    with torch.cuda.device(dev):
+        rc = lib.cr_heater_blend_f32(_ptr(gate), gate.shape[1], _ptr(expert), _ptr(Vin), float(keep), float(one_minus_keep), n, d,
+                                     _ptr(out), _stream(dev))
+    _lib.check(rc, "cr_heater_blend_f32")
+    return out

@@ -1,0 +1,159 @@
+"""Full-catalogue scoring: eval plans and the fused scorer front end.
+
+``EvalPlan`` replaces ``BaseColdStartTrainer._get_eval_cache`` (model/BaseRecommender.py:109-151):
+instead of one LongTensor of train items per eval user plus a LongTensor column mask, it holds one
+CSR (mask_rowptr int64, mask_col int32) over the eval users, one CSR of their ground truth and a
+per-item flag byte (bit 0 = cold item, bit 1 = warm item).  ``FullRankScorer`` replaces the body of
+``_evaluate`` (:170-182): ``batch_predict`` + mask writes + ``torch.topk``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+
+FLAG_COLD = 1   # item listed in data.mapped_cold_item_idx
+FLAG_WARM = 2   # item listed in data.mapped_warm_item_idx
+GROUP_UNFLAGGED = -1   # item group: rows of the item table listed in neither
+
+
+def flag_exclude_for(cold_object: str, data_type: str) -> int:
+    """Which item flag the reference masks (model/BaseRecommender.py:130-143): item-cold runs mask
+    cold items in the 'warm' setting and warm items in the 'cold' setting; nothing otherwise."""
+    if cold_object != 'item':
+        return 0
+    return {'warm': FLAG_COLD, 'cold': FLAG_WARM}.get(data_type, 0)
+
+
+def item_flags_from(data, device) -> torch.Tensor:
+    flags = np.zeros(int(data.item_num), dtype=np.uint8)
+    flags[np.asarray(data.mapped_cold_item_idx, dtype=np.int64)] |= FLAG_COLD
+    flags[np.asarray(data.mapped_warm_item_idx, dtype=np.int64)] |= FLAG_WARM
+    return torch.from_numpy(flags).to(device)
+
+
+def _csr_from_lists(rows: Sequence[np.ndarray]):
+    lens = np.fromiter((len(r) for r in rows), dtype=np.int64, count=len(rows))
+    rowptr = np.zeros(len(rows) + 1, dtype=np.int64)
+    np.cumsum(lens, out=rowptr[1:])
+    col = np.concatenate(rows).astype(np.int32) if len(rows) and rowptr[-1] else np.zeros(0, dtype=np.int32)
+    return rowptr, col
+
+
+@dataclass
+class EvalPlan:
+    users: list                    # raw eval-user ids in ground-truth dict order (BaseRecommender.py:115)
+    user_ids: torch.Tensor         # int32 [n_q] dense user ids
+    mask_rowptr: torch.Tensor      # int64 [n_q+1]   train items of each eval user (:117-128)
+    mask_col: torch.Tensor         # int32, ascending within a row
+    gt_rowptr: torch.Tensor        # int64 [n_q+1]   ground-truth items, dense ids, ascending within a row
+    gt_col: torch.Tensor
+    flag_exclude: int              # 0 | FLAG_COLD | FLAG_WARM (:130-143)
+
+    @property
+    def n_q(self) -> int:
+        return self.user_ids.numel()
+
+    @classmethod
+    def from_data(cls, data, data_set: Dict, data_type: str, cold_object: str, device) -> "EvalPlan":
+        """From a ColdStartDataBuilder-like object (``user``/``item`` maps, ``training_set_u``)."""
+        users = list(data_set.keys())
+        umap, imap = data.user, data.item
+        try:
+            uids = np.fromiter((umap[u] for u in users), dtype=np.int32, count=len(users))
+        except KeyError as e:          # util/databuilder.py:289-296
+            raise Exception(f"user {e.args[0]} not in current id table")
+        mask_rows, gt_rows = [], []
+        for u in users:
+            tr = data.training_set_u[u] if u in data.training_set_u else {}
+            mask_rows.append(np.sort(np.fromiter((imap[i] for i in tr), dtype=np.int64, count=len(tr))))
+            g = data_set[u]
+            gt_rows.append(np.sort(np.fromiter((imap[i] for i in g), dtype=np.int64, count=len(g))))
+        mrp, mc = _csr_from_lists(mask_rows)
+        grp, gc = _csr_from_lists(gt_rows)
+        t = lambda a: torch.from_numpy(a).to(device)
+        return cls(users, t(uids), t(mrp), t(mc), t(grp), t(gc), flag_exclude_for(cold_object, data_type))
+
+    @classmethod
+    def from_arrays(cls, user_ids, mask_rowptr, mask_col, gt_rowptr, gt_col, flag_exclude=0, users=None) -> "EvalPlan":
+        return cls(users if users is not None else None, user_ids, mask_rowptr, mask_col, gt_rowptr, gt_col, int(flag_exclude))
+
+
+class FullRankScorer:
+    """score -> train mask -> flag mask -> top-K for every eval user against the whole catalogue.
+
+    ``tables`` generalises ``batch_predict``: a list of (user_table, item_table, item_group) where
+    item_group is None (all items), FLAG_WARM / FLAG_COLD (only items carrying that flag) or
+    GROUP_UNFLAGGED (items carrying neither):
+      - the canonical ``user_emb[users] @ item_emb.T`` (model/MF.py:58-63)   -> [(U, I, None)]
+      - ALDI's dual user tables (model/ALDI.py:149-160)                     -> [(Uw, I, FLAG_WARM), (Uc, I, FLAG_COLD)]
+      - VBPR/AMR's sum of two products (model/VBPR.py:68-75)                 -> [([P|P2], [Q|Q2], None)]
+    Each table pair is swept by the fused kernel; several lists are merged by (score desc, id asc).
+    Items excluded by the warm/cold column mask are compacted away before the sweep when that is
+    cheaper; lists that come up short because of it are completed with masked ids at -1e9, as the
+    reference's top-K would show.
+    """
+
+    def __init__(self, K: int, precision: int = ops.SCORE_TF32_CHECKED):
+        self.K, self.precision = int(K), precision
+        self._compact_cache = {}
+        self.n_refined: List[torch.Tensor] = []      # device counters of the last topk() call
+
+    def _compact(self, item_tab: torch.Tensor, keep_mask: torch.Tensor, key):
+        ck = (item_tab.data_ptr(), item_tab._version, tuple(item_tab.shape), key)
+        hit = self._compact_cache.get(ck)
+        if hit is None:
+            gids = torch.nonzero(keep_mask, as_tuple=False).flatten().to(torch.int32)
+            hit = (ops.gather_rows(item_tab, gids), gids)
+            if len(self._compact_cache) >= 4:        # tables change every epoch: keep the cache tiny
+                self._compact_cache.clear()
+            self._compact_cache[ck] = hit
+        return hit
+
+    def topk(self, tables, plan: EvalPlan, item_flags: Optional[torch.Tensor] = None):
+        K, excl = self.K, plan.flag_exclude
+        if excl and item_flags is None:
+            raise ValueError("this plan masks warm/cold items: item_flags is required")
+        n_items_total = tables[0][1].shape[0]
+        if n_items_total < K:
+            raise ValueError(f"top-{K} over {n_items_total} items (torch.topk raises here as well)")
+        lists, compacted = [], False
+        self.n_refined = []
+        for user_tab, item_tab, group in tables:
+            tab, gids, kflags, kexcl = item_tab, None, None, 0
+            if group is not None:
+                if item_flags is None:
+                    raise ValueError("item groups need item_flags")
+                keep = (item_flags & (FLAG_WARM | FLAG_COLD)) == 0 if group == GROUP_UNFLAGGED else (item_flags & group) != 0
+                if excl:
+                    keep = keep & ((item_flags & excl) == 0)
+                tab, gids = self._compact(item_tab, keep, (group, excl))
+                compacted = True
+            elif excl:
+                keep = (item_flags & excl) == 0
+                if int(keep.sum()) < 0.9 * item_tab.shape[0]:      # skipping flagged items outright is cheaper
+                    tab, gids = self._compact(item_tab, keep, (0, excl))
+                    compacted = True
+                else:
+                    kflags, kexcl = item_flags, excl
+            if tab.shape[0] == 0:
+                continue
+            s, i, nref = ops.score_topk(user_tab, tab, K, user_ids=plan.user_ids, item_gids=gids, mask_rowptr=plan.mask_rowptr,
+                                        mask_col=plan.mask_col, item_flags=kflags, flag_exclude=kexcl, precision=self.precision)
+            self.n_refined.append(nref)
+            lists.append((s, i))
+        if not lists:
+            s = torch.full((plan.n_q, K), float("-inf"), dtype=torch.float32, device=plan.user_ids.device)
+            i = torch.full((plan.n_q, K), -1, dtype=torch.int32, device=plan.user_ids.device)
+        elif len(lists) == 1:
+            s, i = lists[0]
+        else:
+            s, i = ops.topk_merge(torch.stack([l[0] for l in lists]), torch.stack([l[1] for l in lists]))
+        if compacted:
+            ops.fill_masked(s, i, n_items_total, item_flags=item_flags if excl else None, flag_exclude=excl,
+                            mask_rowptr=plan.mask_rowptr, mask_col=plan.mask_col)
+        return s, i

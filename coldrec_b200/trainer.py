@@ -1,0 +1,258 @@
+"""The reference's trainer API (model/BaseRecommender.py) with the evaluation hot path on the GPU.
+
+``BaseColdStartTrainer`` keeps the constructor, attributes and method names of the reference class
+(``train`` / ``predict`` / ``batch_predict`` / ``save`` abstract; ``_evaluate`` / ``valid`` / ``test`` /
+``full_evaluation`` / ``fast_evaluation`` / ``run`` concrete) so the 26 ``model/*.py`` trainers can
+subclass it unchanged.  Differences, all inside the hot path:
+
+  * ``_evaluate`` (reference :153-188) does not call ``batch_predict``; it asks the model for its score
+    tables (``get_score_tables``, by default ``[(get_user_emb(), get_item_emb(), None)]``) and runs the
+    fused scorer, returning a lazily materialised ``RecList``.
+  * ``ranking_evaluation`` is the device reduction of ``coldrec_b200.evaluator``.
+  * ``get_user_emb`` / ``get_item_emb`` are added as accessors over ``self.user_emb`` / ``self.item_emb``
+    (in the reference only USIMCore has them, model/USIM.py:602,628).
+
+``FusedEvalMixin`` carries the same overrides for grafting onto the reference's own base class:
+``class MF(FusedEvalMixin, reference.BaseColdStartTrainer)`` — see INTEGRATION.md.
+"""
+from __future__ import annotations
+
+import math
+import time
+from abc import ABC, abstractmethod
+from typing import Dict, List, Tuple
+
+import torch
+
+from . import ops
+from .evaluator import RecList, ranking_evaluation
+from .scoring import FLAG_COLD, FLAG_WARM, GROUP_UNFLAGGED, EvalPlan, FullRankScorer, item_flags_from
+
+
+class FusedEvalMixin:
+    """Overrides of the evaluation path; expects the attributes set by BaseColdStartTrainer.__init__."""
+
+    score_precision = ops.SCORE_TF32_CHECKED
+
+    # ---- accessors named by the north star -----------------------------------------------------
+    def get_user_emb(self) -> torch.Tensor:
+        return self.user_emb
+
+    def get_item_emb(self) -> torch.Tensor:
+        return self.item_emb
+
+    def get_score_tables(self):
+        """[(user_table, item_table, item_group)] — see FullRankScorer.  Models whose ``batch_predict`` is
+        not a single inner product override this (ALDI, VBPR/AMR below)."""
+        return [(self.get_user_emb(), self.get_item_emb(), None)]
+
+    # ---- the hot path ---------------------------------------------------------------------------
+    def _fused_state(self):
+        st = self.__dict__.get("_fused")
+        if st is None:
+            dev = torch.device(self.device)
+            if dev.type != "cuda":
+                raise RuntimeError("coldrec_b200 evaluates on a B200 only: config.device must be a CUDA device "
+                                   "(there is no CPU fallback)")
+            st = {"scorer": FullRankScorer(self.max_N, self.score_precision), "plans": {},
+                  "flags": item_flags_from(self.data, dev) if self.args.cold_object == 'item' else None, "device": dev}
+            self.__dict__["_fused"] = st
+        return st
+
+    def _get_eval_cache(self, data_set: Dict, data_type: str) -> EvalPlan:
+        """Reference :109-151, memoised on the same key; one CSR + flags instead of per-user tensors."""
+        st = self._fused_state()
+        key = (id(data_set), data_type, str(self.device), self.args.cold_object)
+        plan = st["plans"].get(key)
+        if plan is None:
+            plan = EvalPlan.from_data(self.data, data_set, data_type, self.args.cold_object, st["device"])
+            st["plans"][key] = plan
+        return plan
+
+    def _evaluate(self, data_set: Dict, data_type: str = 'all') -> RecList:
+        """Reference :153-188: full ranking of every eval user -> {user: [(item, score) x max_N]}."""
+        st = self._fused_state()
+        plan = self._get_eval_cache(data_set, data_type)
+        tables = []
+        for ut, it, grp in self.get_score_tables():
+            ut = ut.detach().to(device=st["device"], dtype=torch.float32).contiguous()
+            it = it.detach().to(device=st["device"], dtype=torch.float32).contiguous()
+            tables.append((ut, it, grp))
+        scores, ids = st["scorer"].topk(tables, plan, st["flags"])
+        rec = RecList(plan, scores, ids, self.data.id2item)
+        rec._gt_id = id(data_set)
+        return rec
+
+    def _ranking_evaluation(self, gt, rec_list, topN):
+        return ranking_evaluation(gt, rec_list, topN, item_map=self.data.item, device=self._fused_state()["device"])
+
+
+class BaseColdStartTrainer(FusedEvalMixin, ABC):
+    """Mirror of model/BaseRecommender.py:13-370 (same constructor contract: ``config.args``,
+    ``config.data``, ``config.device``)."""
+
+    def __init__(self, config):
+        self.config = config
+        self.args = config.args
+        self.data = config.data
+        self.bestPerformance = []
+        self.topN = [int(num) for num in self.args.topN.split(',')]
+        self.max_N = max(self.topN)
+        self.model_name = self.args.model
+        self.dataset_name = self.args.dataset
+        self.emb_size = self.args.emb_size
+        self.maxEpoch = self.args.epochs
+        self.batch_size = self.args.bs
+        self.lr = self.args.lr
+        self.reg = self.args.reg
+        self.device = self.config.device
+        self.result = []
+        self.early_stop_flag = self.args.early_stop != 0
+        if self.early_stop_flag:
+            self.early_stop_patience = self.args.early_stop
+            self.max_early_stop_patience = self.args.early_stop
+        self.epochs_ran = 0
+        self.eval_every = max(1, int(getattr(self.args, 'eval_every', 1)))
+
+    def print_basic_info(self):
+        print('*' * 80)
+        for k, v in (('Model: ', self.model_name), ('Dataset: ', self.dataset_name), ('Embedding Dimension:', self.emb_size),
+                     ('Maximum Epoch:', self.maxEpoch), ('Learning Rate:', self.lr), ('Batch Size:', self.batch_size)):
+            print(k, v)
+        print('*' * 80)
+
+    def timer(self, start=True):
+        if start:
+            self.train_start_time = time.time()
+        else:
+            self.train_end_time = time.time()
+
+    @abstractmethod
+    def train(self) -> None: ...
+
+    @abstractmethod
+    def save(self) -> None: ...
+
+    def predict(self, u):
+        """Scores of one user over all items (reference abstract :74; MF.py:52-56 given here as default)."""
+        with torch.no_grad():
+            uid = self.data.get_user_id(u)
+            return torch.matmul(self.get_user_emb()[uid], self.get_item_emb().transpose(0, 1)).cpu().numpy()
+
+    def batch_predict(self, users):
+        """Dense (len(users), item_num) scores (reference abstract :87).  Kept for API compatibility with
+        callers outside evaluation; ``_evaluate`` never materialises this matrix."""
+        with torch.no_grad():
+            uids = torch.as_tensor(self.data.get_user_id_list(users), device=self.get_user_emb().device)
+            return torch.matmul(self.get_user_emb()[uids], self.get_item_emb().transpose(0, 1))
+
+    def _set(self, prefix: str, kind: str):
+        name = {'warm': 'warm', 'cold': 'cold', 'all': 'overall'}.get(kind)
+        if name is None:
+            raise ValueError(f'Invalid {prefix} type!')
+        return getattr(self.data, f'{name}_{prefix}_set')
+
+    def valid(self, valid_type: str = 'all'):
+        return self._evaluate(self._set('valid', valid_type), valid_type)
+
+    def test(self, test_type: str = 'all'):
+        return self._evaluate(self._set('test', test_type), test_type)
+
+    def full_evaluation(self, rec_list, test_type: str = 'warm') -> None:
+        test_set = self._set('test', test_type)
+        self.result, test_performance = self._ranking_evaluation(test_set, rec_list, self.topN)
+        setattr(self, {'warm': 'warm', 'cold': 'cold', 'all': 'overall'}[test_type] + '_test_results', test_performance)
+        print('*' * 80)
+        print(f'[{test_type} setting] The result of %s:\n%s' % (self.model_name, ''.join(self.result)))
+
+    @staticmethod
+    def _metrics_dict_from_measure(measure: List[str]) -> Dict[str, float]:
+        out = {}
+        for m in measure[1:]:
+            k, v = m.strip().split(':')
+            out[k] = float(v)
+        return out
+
+    @staticmethod
+    def _metrics_all_finite(performance: Dict[str, float]) -> bool:
+        return all(math.isfinite(v) for v in performance.values())
+
+    def fast_evaluation(self, epoch: int, valid_type: str = 'all') -> List[str]:
+        """Reference :268-351: validate at max(topN); strict NDCG improvement saves and resets patience."""
+        valid_set = self._set('valid', valid_type)
+        print(f'Evaluating the model under the {valid_type} setting...')
+        rec_list = self.valid(valid_type)
+        measure, _ = self._ranking_evaluation(valid_set, rec_list, [self.max_N])
+        performance = self._metrics_dict_from_measure(measure)
+        finite = self._metrics_all_finite(performance)
+        if self.bestPerformance:
+            if finite and performance['NDCG'] > self.bestPerformance[1]['NDCG']:      # strict improvement, :306-316
+                self.bestPerformance = [epoch + 1, performance]
+                self.save()
+                if self.early_stop_flag:
+                    self.early_stop_patience = self.max_early_stop_patience
+            else:
+                if self.early_stop_flag:
+                    self.early_stop_patience -= 1
+                if not finite:
+                    print('Warning: validation metrics are non-finite; early-stop patience decreased, best checkpoint unchanged.')
+        elif finite:                                                                  # :318-321
+            self.bestPerformance = [epoch + 1, performance]
+            self.save()
+        elif self.early_stop_flag:                                                    # :322-327
+            self.early_stop_patience -= 1
+            print('Warning: first validation has non-finite metrics; best checkpoint not initialized yet.')
+
+        print('-' * 120)
+        print('Performance ' + ' (Top-' + str(self.max_N) + ' Recommendation)')
+        measure_lines = [m.strip() for m in measure[1:]]
+        print('*Current Performance*')
+        print('Epoch:', str(epoch + 1) + ',', '  |  '.join(measure_lines))
+        if self.bestPerformance:
+            bp = '  |  '.join(k + ':' + str(self.bestPerformance[1][k]) for k in ('Hit Ratio', 'Precision', 'Recall', 'NDCG'))
+            print(f'*Best {valid_type} Performance* ')
+            print('Epoch:', str(self.bestPerformance[0]) + ',', bp)
+        else:
+            print(f'*Best {valid_type} Performance* not initialized (waiting for finite validation).')
+        if self.early_stop_flag:
+            if self.early_stop_patience <= 0:
+                print(f"Stopping early at epoch {epoch + 1}.")
+            else:
+                print(f"Early stopping patience left: {self.early_stop_patience}.")
+        print('-' * 120)
+        return measure_lines
+
+    def run(self) -> None:
+        """Reference :353-370: train, then test + evaluate under all / cold / warm."""
+        self.print_basic_info()
+        print('Training Model...')
+        self.train()
+        if getattr(self, 'epochs_ran', 0) == 0 and self.maxEpoch > 0:
+            self.epochs_ran = self.maxEpoch
+        for test_type in ['all', 'cold', 'warm']:
+            print('*' * 80)
+            print(f'Testing under [{test_type}] setting...')
+            rec_list = self.test(test_type=test_type)
+            print(f'Evaluating under [{test_type}] setting...')
+            self.full_evaluation(rec_list, test_type=test_type)
+
+
+class AldiScoreTables:
+    """``get_score_tables`` for ALDI (model/ALDI.py:149-160): warm items are scored with
+    ``warm_user_emb``, cold items with ``cold_user_emb``; rows of the item table in neither list keep
+    the zero the reference initialises the score matrix with."""
+
+    def get_score_tables(self):
+        tables = [(self.warm_user_emb, self.item_emb, FLAG_WARM), (self.cold_user_emb, self.item_emb, FLAG_COLD)]
+        flags = self._fused_state()["flags"]
+        if bool(((flags & (FLAG_WARM | FLAG_COLD)) == 0).any()):
+            tables.append((torch.zeros_like(self.warm_user_emb), self.item_emb, GROUP_UNFLAGGED))
+        return tables
+
+
+class TwoProductScoreTables:
+    """``get_score_tables`` for VBPR / AMR (model/VBPR.py:68-75, model/AMR.py:68-76):
+    P.Q^T + P2.Q2^T == [P|P2].[Q|Q2]^T, one sweep at d = d1 + d2."""
+
+    def get_score_tables(self):
+        return [(torch.cat([self.user_emb_main, self.user_emb_aux], 1), torch.cat([self.item_emb_main, self.item_emb_aux], 1), None)]

@@ -1,0 +1,163 @@
+/*
+ * coldrec_b200.h — C ABI of the B200-native embedding-generation-and-scoring path of ColdRec.
+ *
+ * The reference (YuanchenBei/ColdRec) is pure Python; the "FFI" a maintainer binds is therefore a
+ * ctypes stub.  Every entry point below replaces a torch call site of the
+ * reference, cited as file:line relative to the ColdRec tree.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.  All pointers are DEVICE pointers on the
+ *     current CUDA device unless a parameter says "host".
+ *   - The caller owns every buffer including workspaces; functions never allocate, free or retain
+ *     pointers, and are asynchronous on `stream` (a cudaStream_t passed as void*).
+ *   - Return value: CR_OK (0) or a negative CR_ERR_* code; no C++ exception crosses the ABI.
+ *   - Tables are fp32 row-major, rows 16-byte aligned (d % 4 == 0); ids are int32; CSR row pointers int64.
+ *   - There is NO CPU fallback: without an sm_100 device every compute call returns CR_ERR_NO_DEVICE.
+ */
+#ifndef COLDREC_B200_H
+#define COLDREC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CR_API __attribute__((visibility("default")))
+#else
+#define CR_API
+#endif
+
+#define CR_OK 0
+#define CR_ERR_ARG (-1)         /* null pointer / negative size / inconsistent shape            */
+#define CR_ERR_ALIGN (-2)       /* pointer or leading dimension not 16-byte aligned             */
+#define CR_ERR_UNSUPPORTED (-3) /* d, K or another parameter outside the supported set           */
+#define CR_ERR_WORKSPACE (-4)   /* workspace smaller than cr_*_workspace_bytes() says            */
+#define CR_ERR_CUDA (-5)        /* a CUDA runtime/driver call failed (see cr_last_cuda_error)    */
+#define CR_ERR_NO_DEVICE (-6)   /* no CUDA device, or the current device is not sm_100           */
+
+#define CR_MAX_K 64             /* largest top-K per call (reference default max(topN)=20)       */
+#define CR_MASK_SCORE (-1.0e9f) /* model/BaseRecommender.py:177,180  (`-10e8`)                   */
+
+#define CR_SCORE_EXACT_F32 0    /* fp32 FFMA scoring, no approximation anywhere                  */
+#define CR_SCORE_TF32_CHECKED 1 /* tcgen05 TF32 selection + exact fp32 rescoring + margin check  */
+
+#define CR_ACT_NONE 0
+#define CR_ACT_TANH 1
+#define CR_ACT_LEAKY_RELU 2     /* slope 0.01 (torch F.leaky_relu default), model/NGCF.py:99     */
+
+CR_API const char *cr_strerror(int code);
+CR_API const char *cr_last_cuda_error(void); /* text of the last CUDA error seen by this library (thread-local) */
+CR_API int cr_version(void);
+CR_API int cr_device_check(void);            /* CR_OK iff the current device is compute capability 10.x */
+
+/* ------------------------------------------------------------------------------------------------
+ * K3 — CSR SpMM with fused layer accumulation.
+ * Replaces `torch.sparse.mm(self.sparse_norm_adj, ego_embeddings)` (model/LightGCN.py:90,
+ * model/NGCF.py:95, model/SimGCL.py:105, model/XSimGCL.py:111, model/NCL.py:190, model/CGRC.py:70,89,
+ * model/FSGNN.py:363,404,438) and the `torch.stack` + `torch.mean` that follows (LightGCN.py:92-93).
+ *
+ *   y[r,:]   = sum_j val[j] * X[col[j],:]   for j in [rowptr[r], rowptr[r+1])      r in [0, n_rows)
+ *   Y[r,:]   = y[r,:]                                  if Y   != NULL
+ *   acc[r,:] = (acc_beta*acc_in[r,:] + y[r,:]) / acc_div   if acc != NULL   (acc_in == NULL means in place;
+ *                                                           acc_in is not read when acc_beta == 0)
+ *
+ * rowptr/Y/acc describe the caller's LOCAL row block (row-partitioned multi-GPU passes its slice);
+ * X is the full gather source.  val == NULL means all-ones.  `plan` (from cr_spmm_plan) enables the
+ * split path for rows longer than 512 nonzeros; plan == NULL processes every row with one warp.
+ * A plan belongs to one (rowptr, nnz, d) triple and is reused across layers and epochs.
+ * ------------------------------------------------------------------------------------------------ */
+CR_API size_t cr_spmm_plan_bytes(int64_t n_rows, int64_t nnz, int d);
+CR_API int cr_spmm_plan(const int64_t *rowptr, int64_t n_rows, int64_t nnz, int d, void *plan, size_t plan_bytes,
+                 void *stream);
+CR_API int cr_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n_rows, int64_t nnz,
+                    const float *X, int d, float *Y, const float *acc_in, float *acc, float acc_beta, float acc_div,
+                    void *plan, size_t plan_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1 — fused full-catalogue scorer: score -> train mask -> flag mask -> top-K, no score matrix in HBM.
+ * Replaces `batch_predict` (model/MF.py:58-63 and its 21 copies) + the mask writes + `torch.topk`
+ * inside `BaseColdStartTrainer._evaluate` (model/BaseRecommender.py:170-182).
+ *
+ *   query j   = user_tab[user_ids ? user_ids[j] : j, :]                          j in [0, n_q)
+ *   item  p   = item_tab[p, :], global id gid(p) = item_gids ? item_gids[p] : item_id_base + p
+ *   s(j,p)    = CR_MASK_SCORE  if gid(p) is in row j of the CSR (mask_rowptr, mask_col)   [train mask, :175-177]
+ *             = CR_MASK_SCORE  if item_flags[gid(p)] & flag_exclude                      [column mask, :179-180]
+ *             = <query j, item p>  (fp32)                                                [MF.py:62]
+ *   out       = the K best (s desc, gid asc) per query: out_score[j,:], out_id[j,:] (global ids).
+ *
+ * item_gids, when given, must be strictly increasing; mask_col rows must be sorted ascending.
+ * If fewer than K items exist the tail is padded with (-inf, -1).  With CR_SCORE_TF32_CHECKED the
+ * selection runs on tcgen05 TF32 and every returned score is re-computed in fp32; queries whose
+ * TF32 margin could not be proven are re-run exactly inside the same call, and their number is
+ * written to *n_refined (device int32, nullable).
+ * ------------------------------------------------------------------------------------------------ */
+CR_API size_t cr_score_topk_workspace_bytes(int64_t n_q, int64_t n_items, int d, int K, int precision);
+CR_API int cr_score_topk_f32(const float *user_tab, const int32_t *user_ids, int64_t n_q, const float *item_tab,
+                      const int32_t *item_gids, int64_t item_id_base, int64_t n_items, int d,
+                      const int64_t *mask_rowptr, const int32_t *mask_col, const uint8_t *item_flags,
+                      uint8_t flag_exclude, int K, float *out_score, int32_t *out_id, int32_t *n_refined,
+                      int precision, void *workspace, size_t ws_bytes, void *stream);
+
+/* Diagnostic probe of the tcgen05 path: like cr_score_topk_f32 (d = 64, TF32-checked, no masks) and
+ * additionally dumps the raw TF32 scores of the first 256 queries x first 128 items into dbg[256*128]. */
+CR_API int cr_debug_tc_tile(const float *user_tab, int64_t n_q, const float *item_tab, int64_t n_items, int K,
+                            float *out_score, int32_t *out_id, float *dbg, void *workspace, size_t ws_bytes, void *stream);
+
+/* Merge G candidate lists per query (item shards / ALDI's two item groups, model/ALDI.py:149-160 /
+ * per-GPU candidates after the NCCL allgather) into one top-K by (score desc, id asc).
+ * in_score/in_id: [G, n_q, K] (list g of query j at ((g*n_q)+j)*K); ids < 0 are padding. */
+CR_API int cr_topk_merge(const float *in_score, const int32_t *in_id, int G, int64_t n_q, int K, float *out_score,
+                  int32_t *out_id, void *stream);
+
+/* Lists that came up short (trailing ids < 0) because flagged items were compacted away before the sweep:
+ * fill the tail with masked ids at CR_MASK_SCORE, which is what the reference's top-K shows when a query
+ * has fewer than K unmasked items (model/BaseRecommender.py:177-182; which masked ids is unspecified). */
+CR_API int cr_fill_masked(float *out_score, int32_t *out_id, int64_t n_q, int K, int64_t n_items_total,
+                          const uint8_t *item_flags, uint8_t flag_exclude, const int64_t *mask_rowptr,
+                          const int32_t *mask_col, void *stream);
+
+/* dst[j,:] = src[ids[j],:]  — `self.user_emb[users]` (model/MF.py:62) and flag-compaction of item tables. */
+CR_API int cr_gather_rows_f32(const float *src, const int32_t *ids, int64_t n, int d, float *dst, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2 — ranking metrics reduced on device.  Replaces `ranking_evaluation` / `Metric.*`
+ * (util/evaluator.py:9-32, 47-63, 95-115, 153-187).
+ *   topk_id [n_q, K]   sorted top-K global ids per query (ids < 0 ignored)
+ *   gt CSR             row j = ground-truth item ids of query j, sorted ascending
+ *   Ns (host) [nN]     cut-offs, each <= K
+ *   inv_log2 [K]       1/log(n+2, 2); idcg_prefix [K+1]: prefix sums of inv_log2 (both computed by the
+ *                      host exactly as util/evaluator.py:106-109 does, so per-user DCG/IDCG are bit-equal)
+ *   hits [nN, n_q] int32 and dcg [nN, n_q] double per-query outputs (nullable)
+ *   sums [nN, 6] double: sum_hits, sum_gt, sum(hits/|gt|) over |gt|>0, #{|gt|>0}, sum(dcg/idcg) over idcg>0, #{idcg>0}
+ * ------------------------------------------------------------------------------------------------ */
+CR_API size_t cr_rank_metrics_workspace_bytes(int64_t n_q, int nN);
+CR_API int cr_rank_metrics(const int32_t *topk_id, int64_t n_q, int K, const int64_t *gt_rowptr, const int32_t *gt_col,
+                    const int32_t *Ns_host, int nN, const double *inv_log2, const double *idcg_prefix, int32_t *hits,
+                    double *dcg, double *sums, void *workspace, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4 — content->embedding towers.  One fused layer:
+ *   Y[yrow ? yrow[r] : r, :] = act( ([X1[xr,:] | X2[xr,:]] . W^T + bias) * scale + shift ),  xr = xrow ? xrow[r] : r
+ * W is torch nn.Linear layout [n_out, d1+d2]; scale/shift (nullable) carry an eval-mode BatchNorm1d.
+ * Replaces nn.Linear -> BatchNorm1d(eval) -> tanh chains: model/DropoutNet.py:204-212,222-236,
+ * model/Heater.py:143-167,218-222, model/GAR.py:102-107, model/ALDI.py:204-208; the two-segment
+ * input is the `torch.cat((Vin, Vcontent), 1)` of DropoutNet.py:199-202; xrow/yrow are the
+ * `content[cold_idx]` gather and `item_emb[cold_idx] = ...` scatter of GAR.py:44-46 / ALDI.py:96.
+ * ------------------------------------------------------------------------------------------------ */
+CR_API int cr_linear_act_f32(const float *X1, int64_t ld1, int d1, const float *X2, int64_t ld2, int d2, const int32_t *xrow,
+                      int64_t n_rows, const float *W, const float *bias, const float *scale, const float *shift,
+                      int n_out, int act, float *Y, int64_t ldy, const int32_t *yrow, void *stream);
+/* scale = gamma / sqrt(var + eps); shift = beta - mean * scale   (eval BatchNorm1d, DropoutNet.py:226-230) */
+CR_API int cr_bn_fold_f32(const float *gamma, const float *beta, const float *mean, const float *var, float eps, int n,
+                   float *scale, float *shift, void *stream);
+/* out = Vin*keep + tanh(sum_g gate[:,g] * expert) * one_minus_keep   (model/Heater.py:189-198) */
+CR_API int cr_heater_blend_f32(const float *gate, int n_expert, const float *expert, const float *Vin, float keep,
+                        float one_minus_keep, int64_t n_rows, int d, float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COLDREC_B200_H */
