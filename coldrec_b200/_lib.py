@@ -25,6 +25,9 @@ SIGNATURES = {
     "cr_last_cuda_error": (c_char_p, []),
     "cr_version": (c_int, []),
     "cr_device_check": (c_int, []),
+    "cr_launch_count": (ctypes.c_ulonglong, []),
+    "cr_profile_enable": (c_int, [c_int]),
+    "cr_profile_read": (c_int, [c_int, ctypes.POINTER(c_double), ctypes.POINTER(c_int)]),
     "cr_spmm_plan_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "cr_spmm_plan": (c_int, [_P, c_int64, c_int64, c_int, _P, c_size_t, _P]),
     "cr_spmm_csr_f32": (c_int, [_P, _P, _P, c_int64, c_int64, _P, c_int, _P, _P, _P, c_float, c_float, _P, c_size_t, _P]),

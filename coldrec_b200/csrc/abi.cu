@@ -32,9 +32,66 @@ int require_device() {
     return cached_rc;
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
+// ---- tiny event profiler: bench.py brackets the dominant kernel without timing under a profiler ----
+constexpr int kMaxPairs = 512;
+struct ProfTag {
+    cudaEvent_t start[kMaxPairs], stop[kMaxPairs];
+    int created = 0, used = 0;
+};
+static ProfTag g_prof[PROF_TAGS];
+static bool g_prof_on = false;
+
+void prof_start(int tag, cudaStream_t st) {
+    if (!g_prof_on) return;
+    ProfTag& t = g_prof[tag];
+    if (t.used >= kMaxPairs) return;
+    if (t.used >= t.created) {
+        if (cudaEventCreate(&t.start[t.created]) != cudaSuccess || cudaEventCreate(&t.stop[t.created]) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        ++t.created;
+    }
+    cudaEventRecord(t.start[t.used], st);
+}
+void prof_stop(int tag, cudaStream_t st) {
+    if (!g_prof_on) return;
+    ProfTag& t = g_prof[tag];
+    if (t.used >= t.created || t.used >= kMaxPairs) return;
+    cudaEventRecord(t.stop[t.used], st);
+    ++t.used;
+}
+
 }  // namespace cr
 
 extern "C" {
+
+unsigned long long cr_launch_count(void) { return __atomic_load_n(&cr::g_launches, __ATOMIC_RELAXED); }
+
+int cr_profile_enable(int on) {
+    cr::g_prof_on = on != 0;
+    for (int t = 0; t < cr::PROF_TAGS; ++t) cr::g_prof[t].used = 0;
+    return CR_OK;
+}
+
+int cr_profile_read(int tag, double* total_ms, int* launches) {
+    if (tag < 0 || tag >= cr::PROF_TAGS || !total_ms || !launches) return CR_ERR_ARG;
+    cr::ProfTag& t = cr::g_prof[tag];
+    double sum = 0.0;
+    for (int i = 0; i < t.used; ++i) {
+        CR_CUDA_TRY(cudaEventSynchronize(t.stop[i]));
+        float ms = 0.f;
+        CR_CUDA_TRY(cudaEventElapsedTime(&ms, t.start[i], t.stop[i]));
+        sum += ms;
+    }
+    *total_ms = sum;
+    *launches = t.used;
+    return CR_OK;
+}
+
 
 const char* cr_strerror(int code) {
     switch (code) {

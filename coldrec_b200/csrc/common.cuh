@@ -14,6 +14,11 @@ namespace cr {
 // Record a CUDA error for cr_last_cuda_error() and return CR_ERR_CUDA.
 int note_cuda_error(cudaError_t e, const char* where);
 int require_device();   // CR_OK iff current device is sm_100; cached per device
+void count_launch();    // every kernel this library launches is counted (cr_launch_count)
+// Optional CUDA-event brackets around the dominant kernels (cr_profile_*): tag 0 = scoring sweep, 1 = SpMM rows.
+enum { PROF_SCORE_SWEEP = 0, PROF_SPMM_ROWS = 1, PROF_TAGS = 2 };
+void prof_start(int tag, cudaStream_t st);
+void prof_stop(int tag, cudaStream_t st);
 
 #define CR_CUDA_TRY(expr)                                          \
     do {                                                           \
@@ -25,6 +30,7 @@ int require_device();   // CR_OK iff current device is sm_100; cached per device
     do {                                                           \
         cudaError_t _e = cudaGetLastError();                       \
         if (_e != cudaSuccess) return cr::note_cuda_error(_e, name); \
+        cr::count_launch();                                        \
     } while (0)
 
 // One exact-scoring job (score_simt.cu); shared with the TF32 path, which uses it to refine.

@@ -701,6 +701,7 @@ int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_
     sp.mask_rowptr = j.mask_rowptr; sp.mask_col = j.mask_col; sp.item_flags = flags;
     sp.flag_exclude = j.flag_exclude; sp.buf = buf; sp.cnt = cnt; sp.thr = thr; sp.dbg_scores = dbg_scores;
     const unsigned grid = (unsigned)(P.n_utiles * P.S);
+    prof_start(PROF_SCORE_SWEEP, st);
     if (P.ksel == 32) {
         CR_CUDA_TRY(cudaFuncSetAttribute(score_sweep_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::kTotal));
         score_sweep_tc_kernel<32><<<grid, kThreads, SmemLayout::kTotal, st>>>(map_q, map_i, sp);
@@ -709,6 +710,7 @@ int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_
         score_sweep_tc_kernel<64><<<grid, kThreads, SmemLayout::kTotal, st>>>(map_q, map_i, sp);
     }
     CR_LAUNCH_CHECK("score_sweep_tc_kernel");
+    prof_stop(PROF_SCORE_SWEEP, st);
 
     RescoreParams rp{Q, j.item_tab, j.item_gids, j.item_id_base, n_q, P.n_q_pad, P.S, K, P.cap, P.ksel, buf, cnt, thr, norm,
                      part_s, part_i, rflag, rlist, rcount};

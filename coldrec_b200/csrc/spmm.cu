@@ -235,6 +235,7 @@ int launch_spmm(const SpmmArgs& a) {
     const int64_t blocks = (a.n_rows * 32 + kThreads - 1) / kThreads;
     if (blocks > 0x7fffffffLL) return CR_ERR_UNSUPPORTED;
     if (a.n_rows > 0) {
+        cr::prof_start(cr::PROF_SPMM_ROWS, a.stream);
         if (a.val)
             spmm_rows_kernel<LPR, NV, true, BOUNDS><<<(unsigned)blocks, kThreads, 0, a.stream>>>(
                 a.rowptr, a.col, a.val, a.n_rows, a.X4, a.d4, a.Y4, a.acc_in4, a.acc4, a.beta, a.div, long_row);
@@ -242,6 +243,7 @@ int launch_spmm(const SpmmArgs& a) {
             spmm_rows_kernel<LPR, NV, false, BOUNDS><<<(unsigned)blocks, kThreads, 0, a.stream>>>(
                 a.rowptr, a.col, a.val, a.n_rows, a.X4, a.d4, a.Y4, a.acc_in4, a.acc4, a.beta, a.div, long_row);
         CR_LAUNCH_CHECK("spmm_rows_kernel");
+        cr::prof_stop(cr::PROF_SPMM_ROWS, a.stream);
     }
     if (a.hdr) {
         const int grid = 148 * 8;

@@ -1,0 +1,152 @@
+"""One-node multi-GPU layer: one process per GPU, ``torch.distributed`` (NCCL over NVLink) as plumbing.
+
+The reference is single-process / single-device; both hot paths shard naturally:
+
+  * scoring  — the item catalogue is split into contiguous ranges, one per GPU (the user table is
+    replicated).  Every GPU produces a local top-K for *all* eval users with the fused kernel, the
+    (score, id) candidates are exchanged with one all-gather, and each GPU merges the W lists for its
+    own slice of the users by (score desc, id asc) — the merge is order independent, so the ids equal
+    a single-GPU sweep bit for bit.  Metric partial sums are all-reduced (6 doubles per cut-off).
+  * propagation — CSR rows are partitioned by nonzero count; every layer each GPU runs the SpMM on
+    its row block and the new embedding rows are all-gathered to rebuild the gather source.  Node ids
+    are remapped once to a padded (rank, local row) numbering so the all-gather output *is* the next
+    layer's input (no unpack copy).
+
+The compute callables are injectable so the partition / exchange / merge logic is covered on CPU with
+the gloo backend (tests/test_dist_gloo.py); the defaults are the CUDA kernels.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .evaluator import metrics_from_sums
+from .graph import CsrGraph
+from .scoring import EvalPlan
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced [begin, end) of n things for ``rank`` (first n % world shards get one more)."""
+    base, rem = divmod(n, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def partition_rows_by_nnz(rowptr: np.ndarray, world: int) -> List[int]:
+    """Row boundaries b[0]=0 <= ... <= b[world]=n_rows with ~nnz/world nonzeros per block."""
+    n_rows, nnz = len(rowptr) - 1, int(rowptr[-1])
+    bounds = [0]
+    for r in range(1, world):
+        bounds.append(int(np.searchsorted(rowptr, nnz * r / world, side="left")))
+    bounds.append(n_rows)
+    return [min(max(b, bounds[i - 1] if i else 0), n_rows) for i, b in enumerate(bounds)]
+
+
+def _all_gather_stack(t: torch.Tensor, group) -> torch.Tensor:
+    world = dist.get_world_size(group)
+    out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group) if t.is_cuda else \
+        dist.all_gather(list(out.unbind(0)), t.contiguous(), group=group)
+    return out
+
+
+class ShardedFullRankScorer:
+    """Item-sharded full ranking.  ``topk`` returns the merged lists of this rank's user slice."""
+
+    def __init__(self, K: int, precision: int = ops.SCORE_TF32_CHECKED, group=None,
+                 local_topk: Optional[Callable] = None, merge: Optional[Callable] = None, metrics: Optional[Callable] = None):
+        self.K, self.precision, self.group = int(K), precision, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._local_topk = local_topk or self._cuda_local_topk
+        self._merge = merge or ops.topk_merge
+        self._metrics = metrics or (lambda ids, rp, col, Ns: ops.rank_metrics(ids, rp, col, Ns)[0])
+
+    def _cuda_local_topk(self, user_tab, item_tab, item_begin, plan: EvalPlan, item_flags):
+        s, i, _ = ops.score_topk(user_tab, item_tab, self.K, user_ids=plan.user_ids, item_id_base=item_begin,
+                                 mask_rowptr=plan.mask_rowptr, mask_col=plan.mask_col, item_flags=item_flags,
+                                 flag_exclude=plan.flag_exclude if item_flags is not None else 0, precision=self.precision)
+        return s, i
+
+    def user_slice(self, n_q: int) -> Tuple[int, int]:
+        return shard_range(n_q, self.rank, self.world)
+
+    def topk(self, user_tab, item_shard: torch.Tensor, item_begin: int, plan: EvalPlan, item_flags=None):
+        """item_shard = rows [item_begin, item_begin + len) of the item table; plan covers ALL eval users.
+        Returns (scores, ids) [n_slice, K] for users user_slice(plan.n_q) — global item ids."""
+        s, i = self._local_topk(user_tab, item_shard, item_begin, plan, item_flags)
+        if self.world == 1:
+            return s, i
+        gs, gi = _all_gather_stack(s, self.group), _all_gather_stack(i, self.group)   # [W, n_q, K]
+        lo, hi = self.user_slice(plan.n_q)
+        return self._merge(gs[:, lo:hi].contiguous(), gi[:, lo:hi].contiguous())
+
+    def metrics(self, ids_slice: torch.Tensor, plan: EvalPlan, Ns: Sequence[int], rounded: bool = True):
+        """Hit/Precision/Recall/NDCG over all eval users from per-rank partial sums (one all-reduce)."""
+        lo, hi = self.user_slice(plan.n_q) if self.world > 1 else (0, plan.n_q)
+        base = plan.gt_rowptr[lo]
+        rp = (plan.gt_rowptr[lo:hi + 1] - base).contiguous()
+        col = plan.gt_col[int(base):int(plan.gt_rowptr[hi])].contiguous()
+        sums = self._metrics(ids_slice, rp, col, list(Ns))
+        if self.world > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+        return metrics_from_sums(sums.cpu().numpy(), plan.n_q, Ns, rounded)
+
+
+class RowPartitionedGraph:
+    """A square adjacency split by rows over the ranks of ``group`` with padded node numbering.
+
+    Global node n owned by rank r at local offset o gets padded id r * rows_pad + o; the local CSR's
+    column ids are remapped accordingly, so a [W * rows_pad, d] all-gather result is directly the
+    gather source of the next layer.  ``to_padded`` / ``from_padded`` convert embedding tables.
+    """
+
+    def __init__(self, rowptr: np.ndarray, col: np.ndarray, val: Optional[np.ndarray], device, group=None,
+                 spmm: Optional[Callable] = None):
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.n = len(rowptr) - 1
+        self.bounds = partition_rows_by_nnz(np.asarray(rowptr), self.world)
+        sizes = np.diff(self.bounds)
+        self.rows_pad = int(sizes.max()) if self.n else 0
+        owner = np.repeat(np.arange(self.world), sizes)
+        self.padded_of = (owner * self.rows_pad + (np.arange(self.n) - np.asarray(self.bounds)[owner])).astype(np.int64)
+        b, e = self.bounds[self.rank], self.bounds[self.rank + 1]
+        lo, hi = int(rowptr[b]), int(rowptr[e])
+        local_rp = np.zeros(self.rows_pad + 1, dtype=np.int64)          # padded rows are empty
+        local_rp[:e - b + 1] = np.asarray(rowptr[b:e + 1]) - lo
+        local_rp[e - b + 1:] = hi - lo
+        local_col = self.padded_of[np.asarray(col[lo:hi], dtype=np.int64)].astype(np.int32)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        self.local = CsrGraph(t(local_rp), t(local_col), None if val is None else t(np.asarray(val[lo:hi], dtype=np.float32)),
+                              self.world * self.rows_pad, row_begin=self.rank * self.rows_pad)
+        self._spmm = spmm or (lambda g, X, **kw: g.spmm(X, **kw))
+        self._padded_idx = t(self.padded_of)
+
+    def to_padded(self, E: torch.Tensor) -> torch.Tensor:
+        out = torch.zeros((self.world * self.rows_pad, E.shape[1]), dtype=E.dtype, device=E.device)
+        out[self._padded_idx] = E
+        return out
+
+    def from_padded(self, Ep: torch.Tensor) -> torch.Tensor:
+        return Ep[self._padded_idx]
+
+    def propagate(self, E0: torch.Tensor, n_layers: int, include_ego: bool = True) -> torch.Tensor:
+        """LightGCN-family propagation (model/LightGCN.py:86-96) over the row partition.  E0 is the full
+        (N, d) table, replicated; returns the full (N, d) layer mean, identical on every rank."""
+        x = self.to_padded(E0)
+        r0 = self.rank * self.rows_pad
+        count = n_layers + (1 if include_ego else 0)
+        acc = torch.empty((self.rows_pad, E0.shape[1]), dtype=E0.dtype, device=E0.device)
+        for k in range(1, n_layers + 1):
+            last, first = k == n_layers, k == 1
+            y = torch.empty_like(acc)
+            self._spmm(self.local, x, Y=y, acc=acc, acc_in=(x[r0:r0 + self.rows_pad] if (first and include_ego) else None),
+                       acc_beta=(0.0 if (first and not include_ego) else 1.0), acc_div=(float(count) if last else 1.0))
+            if not last:
+                x = _all_gather_stack(y, self.group).reshape(self.world * self.rows_pad, -1) if self.world > 1 else y
+        full = _all_gather_stack(acc, self.group).reshape(self.world * self.rows_pad, -1) if self.world > 1 else acc
+        return self.from_padded(full)

@@ -53,6 +53,13 @@ CR_API const char *cr_last_cuda_error(void); /* text of the last CUDA error seen
 CR_API int cr_version(void);
 CR_API int cr_device_check(void);            /* CR_OK iff the current device is compute capability 10.x */
 
+/* Measurement hooks (bench.py): number of kernels this library has launched so far, and CUDA-event
+ * brackets around the dominant kernels (tag 0 = tcgen05 scoring sweep, tag 1 = SpMM row kernel) recorded
+ * on the launching stream while enabled; cr_profile_read synchronises on the recorded events. */
+CR_API unsigned long long cr_launch_count(void);
+CR_API int cr_profile_enable(int on);
+CR_API int cr_profile_read(int tag, double *total_ms, int *launches);
+
 /* ------------------------------------------------------------------------------------------------
  * K3 — CSR SpMM with fused layer accumulation.
  * Replaces `torch.sparse.mm(self.sparse_norm_adj, ego_embeddings)` (model/LightGCN.py:90,

@@ -1,0 +1,166 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic in coldrec_b200/dist.py: item sharding +
+candidate all-gather + per-slice merge + metric all-reduce, and row-partitioned propagation with padded
+node numbering.  The CUDA kernels are replaced by oracle-backed callables (the injection points exist for
+exactly this); results must equal the single-process oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import coldrec_oracle as O
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _case():
+    rng = np.random.default_rng(123)
+    n_users, n_items, n_q, K = 120, 900, 61, 20
+    U = (rng.standard_normal((n_users, 64)) * 0.2).astype(np.float32)
+    I = (rng.standard_normal((n_items, 64)) * 0.2).astype(np.float32)
+    I[rng.choice(n_items, 40, replace=False)] = I[rng.choice(n_items, 40, replace=False)]      # exact ties
+    uids = rng.choice(n_users, n_q, replace=False).astype(np.int32)
+    rows = [np.sort(rng.choice(n_items, int(rng.integers(0, 30)), replace=False)) for _ in range(n_q)]
+    rowptr = np.zeros(n_q + 1, dtype=np.int64); np.cumsum([len(r) for r in rows], out=rowptr[1:])
+    col = np.concatenate(rows).astype(np.int32)
+    gt = [np.sort(rng.choice(n_items, int(rng.integers(0, 8)), replace=False)) for _ in range(n_q)]
+    gt_rowptr = np.zeros(n_q + 1, dtype=np.int64); np.cumsum([len(r) for r in gt], out=gt_rowptr[1:])
+    gt_col = np.concatenate(gt).astype(np.int32)
+    eu, ei = rng.integers(0, n_users, 3000), rng.integers(0, n_items, 3000)
+    return dict(U=U, I=I, uids=uids, rowptr=rowptr, col=col, gt_rowptr=gt_rowptr, gt_col=gt_col, K=K, eu=eu, ei=ei,
+                n_users=n_users, n_items=n_items)
+
+
+def _sorted_topk(scores, ids, K):
+    """(score desc, id asc) top-K of candidate rows, padding ids < 0 last — the merge kernel's order."""
+    out_s = np.full((scores.shape[0], K), -np.inf, dtype=np.float32)
+    out_i = np.full((scores.shape[0], K), -1, dtype=np.int32)
+    for j in range(scores.shape[0]):
+        valid = ids[j] >= 0
+        order = np.lexsort((ids[j][valid], -scores[j][valid].astype(np.float64)))[:K]
+        out_s[j, :len(order)] = scores[j][valid][order]
+        out_i[j, :len(order)] = ids[j][valid][order]
+    return out_s, out_i
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from coldrec_b200.dist import RowPartitionedGraph, ShardedFullRankScorer, shard_range
+        from coldrec_b200.scoring import EvalPlan
+        c = _case()
+        K = c["K"]
+        Ut, It = torch.from_numpy(c["U"]), torch.from_numpy(c["I"])
+
+        def local_topk(user_tab, item_tab, item_begin, plan, item_flags):
+            # exact (score desc, id asc) local list from oracle scores of this shard
+            n_loc = item_tab.shape[0]
+            s = (user_tab[plan.user_ids.long()] @ item_tab.T).numpy().copy()
+            for j in range(plan.n_q):
+                m = c["col"][c["rowptr"][j]:c["rowptr"][j + 1]] - item_begin
+                s[j, m[(m >= 0) & (m < n_loc)]] = O.MASK_SENTINEL
+            ids = np.broadcast_to(np.arange(item_begin, item_begin + n_loc, dtype=np.int32), s.shape)
+            ts, ti = _sorted_topk(s, ids, K)
+            return torch.from_numpy(ts), torch.from_numpy(ti)
+
+        def merge(gs, gi):
+            W, n, k = gs.shape
+            ts, ti = _sorted_topk(gs.permute(1, 0, 2).reshape(n, W * k).numpy(), gi.permute(1, 0, 2).reshape(n, W * k).numpy(), k)
+            return torch.from_numpy(ts), torch.from_numpy(ti)
+
+        def metrics(ids, rp, col, Ns):
+            n = ids.shape[0]
+            sums = np.zeros((len(Ns), 6))
+            for a, N in enumerate(Ns):
+                for j in range(n):
+                    g = set(col[rp[j]:rp[j + 1]].tolist())
+                    row = ids[j, :N].tolist()
+                    hits = len(g.intersection(row))
+                    dcg = sum(1.0 / np.log2(k + 2) for k, it in enumerate(row) if it in g)
+                    idcg = sum(1.0 / np.log2(k + 2) for k in range(min(len(g), N)))
+                    sums[a] += [hits, len(g), hits / len(g) if g else 0, 1 if g else 0, dcg / idcg if idcg else 0, 1 if idcg else 0]
+            return torch.from_numpy(sums)
+
+        plan = EvalPlan.from_arrays(torch.from_numpy(c["uids"]), torch.from_numpy(c["rowptr"]), torch.from_numpy(c["col"]),
+                                    torch.from_numpy(c["gt_rowptr"]), torch.from_numpy(c["gt_col"]))
+        sc = ShardedFullRankScorer(K, group=None, local_topk=local_topk, merge=merge, metrics=metrics)
+        b, e = shard_range(c["n_items"], rank, world)
+        s, i = sc.topk(Ut, It[b:e], b, plan)
+        perf = sc.metrics(i, plan, [10, 20], rounded=False)
+        lo, hi = sc.user_slice(plan.n_q)
+
+        adj = O.normalize_graph_mat(O.bipartite_adjacency(c["eu"], c["ei"], c["n_users"], c["n_items"])).tocsr()
+        adj.sort_indices()
+
+        def cpu_spmm(g, X, Y=None, acc=None, acc_in=None, acc_beta=1.0, acc_div=1.0):
+            A = sp.csr_matrix((g.val.numpy(), g.col.numpy(), g.rowptr.numpy()), shape=(g.n_rows, g.n_cols))
+            y = torch.from_numpy(A @ X.numpy())
+            if Y is not None:
+                Y.copy_(y)
+            if acc is not None:
+                src = acc_in if acc_in is not None else acc
+                acc.copy_(((acc_beta * src + y) if acc_beta else y) / acc_div)
+
+        G = RowPartitionedGraph(adj.indptr.astype(np.int64), adj.indices.astype(np.int64), adj.data.astype(np.float32), "cpu",
+                                spmm=cpu_spmm)
+        E0 = torch.cat([Ut, It])
+        out = {}
+        for ego in (True, False):
+            out[ego] = G.propagate(E0, 3, include_ego=ego).numpy()
+        ret[rank] = dict(s=s.numpy(), i=i.numpy(), lo=lo, hi=hi, perf=perf, prop=out, bounds=G.bounds)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_scoring_and_partitioned_propagation_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    c = _case()
+    K = c["K"]
+    Ut, It = torch.from_numpy(c["U"]), torch.from_numpy(c["I"])
+    # single-process truth with the same deterministic order
+    s_full = (Ut[torch.from_numpy(c["uids"]).long()] @ It.T).numpy().copy()
+    for j in range(len(c["uids"])):
+        s_full[j, c["col"][c["rowptr"][j]:c["rowptr"][j + 1]]] = O.MASK_SENTINEL
+    ids = np.broadcast_to(np.arange(c["n_items"], dtype=np.int32), s_full.shape)
+    ts, ti = _sorted_topk(s_full, ids, K)
+    covered = 0
+    for r in range(world):
+        lo, hi = ret[r]["lo"], ret[r]["hi"]
+        assert np.array_equal(ret[r]["i"], ti[lo:hi]), "sharded ids must equal the single sweep bit for bit"
+        assert np.allclose(ret[r]["s"], ts[lo:hi], atol=1e-6)
+        covered += hi - lo
+    assert covered == len(c["uids"])
+    want = O.metrics_from_topk(ti.astype(np.int64), c["gt_rowptr"], c["gt_col"].astype(np.int64), [10, 20])
+    for r in range(world):
+        assert np.allclose(ret[r]["perf"], want, atol=1e-9), "all-reduced metrics must equal the global ones on every rank"
+    adj = O.normalize_graph_mat(O.bipartite_adjacency(c["eu"], c["ei"], c["n_users"], c["n_items"]))
+    for ego in (True, False):
+        ru, ri = O.propagate(adj, Ut, It, 3, include_ego=ego)
+        ref = torch.cat([ru, ri]).numpy()
+        for r in range(world):
+            assert np.abs(ret[r]["prop"][ego] - ref).max() <= 1e-5 * np.abs(ref).max()
+    assert ret[0]["bounds"] == ret[1]["bounds"] and ret[0]["bounds"][0] == 0
+
+
+def test_partition_helpers():
+    from coldrec_b200.dist import partition_rows_by_nnz, shard_range
+    assert [shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert shard_range(3, 3, 4) == (3, 3)
+    rowptr = np.array([0, 100, 100, 101, 150, 200, 200, 400])
+    b = partition_rows_by_nnz(rowptr, 4)
+    assert b[0] == 0 and b[-1] == 7 and all(x <= y for x, y in zip(b, b[1:]))
+    nnz = [rowptr[b[i + 1]] - rowptr[b[i]] for i in range(4)]
+    assert max(nnz) <= 200

@@ -194,3 +194,19 @@ def test_towers():
                                         t(g[pre + "fc2.weight"]), t(g[pre + "fc2.bias"]))
     assert np.allclose(tower("aldi_u.", U).numpy(), g["aldi_user_out"], atol=1e-6, rtol=0)
     assert np.allclose(tower("aldi_i.", C[cold]).numpy(), g["aldi_cold_item_out"], atol=1e-6, rtol=0)
+
+
+def test_chunked_dense_eval_equals_unchunked():
+    rng = np.random.default_rng(17)
+    U = torch.from_numpy((rng.standard_normal((300, 64)) * 0.2).astype(np.float32))
+    I = torch.from_numpy((rng.standard_normal((5000, 64)) * 0.2).astype(np.float32))
+    uids = rng.choice(300, 150, replace=False)
+    rows = [np.sort(rng.choice(5000, int(rng.integers(0, 60)), replace=False)) for _ in uids]
+    rowptr = np.zeros(len(uids) + 1, dtype=np.int64); np.cumsum([len(r) for r in rows], out=rowptr[1:])
+    col = np.concatenate(rows).astype(np.int64)
+    cmask = rng.choice(5000, 1000, replace=False)
+    for cm in (None, cmask):
+        s0, i0 = O.evaluate_topk_dense(O.score_mf(U, I), uids, rowptr, col, cm, 20, 64)
+        s1, i1 = O.evaluate_topk_dense_chunked(U, I, uids, rowptr, col, cm, 20, user_batch=37, item_chunk=777)
+        assert np.allclose(s0, s1, atol=1e-6, rtol=0)
+        assert (i0 == i1).mean() > 0.999
