@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py — full-rank users/sec (top-20 over the catalogue) and LightGCN edges/sec on B200.
+
+    python bench.py --gpus 1 --steps 8 --warmup 3                       # one GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   # N GPUs, one rank each
+    python bench.py --impl reference ...                                # the reference's CPU path (oracle port), rank 0
+
+Workload (BASELINE.json configs[4] and configs[3], synthetic, seeded):
+  scoring   1M users x 10M items, d=64, K=20, ~100 train-masked items and 10 ground-truth items per user.
+            A step = one eval batch of 65,536 x N users against the whole catalogue: fused score + train mask +
+            top-20 + Hit/Precision/Recall/NDCG@{10,20} reduction.  N GPUs shard the catalogue (10M/N items each),
+            exchange (score,id) candidates over NCCL and merge; per-GPU work is constant -> weak scaling.
+  lightgcn  1M users + 10M items, 100M interactions (nnz(A) ~ 2e8), 3-layer propagation with fused layer mean.
+Inputs are larger than L2 (item shard >= 320 MB, embedding table 2.8 GB), so no explicit L2 flush is needed.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_USERS, N_ITEMS, D, K, TOPN = 1_000_000, 10_000_000, 64, 20, [10, 20]
+USERS_PER_STEP = 65_536
+MASK_PER_USER, GT_PER_USER = 100, 10
+GRAPH_EDGES, LAYERS = 100_000_000, 3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="both", choices=["both", "score", "lightgcn"])
+    ap.add_argument("--users-per-step", type=int, default=USERS_PER_STEP)
+    ap.add_argument("--n-items", type=int, default=N_ITEMS)
+    ap.add_argument("--n-users", type=int, default=N_USERS)
+    ap.add_argument("--graph-edges", type=int, default=GRAPH_EDGES)
+    ap.add_argument("--cpu-sample-users", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------- helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING a timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(self.NAMES, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if x > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except OSError:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def make_step_plans(n_steps, n_q, n_users, n_items, seed, device):
+    """Per step: eval user ids, train-mask CSR (MASK_PER_USER sorted item ids per user), ground-truth CSR."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    plans = []
+    mrp = torch.arange(0, (n_q + 1) * MASK_PER_USER, MASK_PER_USER, device=device, dtype=torch.int64)
+    grp = torch.arange(0, (n_q + 1) * GT_PER_USER, GT_PER_USER, device=device, dtype=torch.int64)
+    for s in range(n_steps):
+        uids = ((torch.arange(n_q, device=device, dtype=torch.int64) + s * n_q) % n_users).to(torch.int32)
+        # distinct sorted ids per row: sort random draws and nudge duplicates apart
+        def rows(per):
+            x = torch.sort(torch.randint(0, n_items - per, (n_q, per), device=device, generator=g), dim=1).values
+            return (x + torch.arange(per, device=device)).to(torch.int32).flatten().contiguous()
+        plans.append(dict(user_ids=uids, mask_rowptr=mrp, mask_col=rows(MASK_PER_USER), gt_rowptr=grp, gt_col=rows(GT_PER_USER)))
+    return plans
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def max_over_ranks(x, device, world):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world, device):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier(device_ids=[device.index])
+    torch.cuda.synchronize(device)
+
+
+# ------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import coldrec_b200 as cr
+    from coldrec_b200 import _lib, ops
+    from coldrec_b200.dist import ShardedFullRankScorer, shard_range
+    from coldrec_b200.scoring import EvalPlan, HostBatchEvaluator
+
+    rank, local_rank, world = dist_env()
+    if args.gpus != world:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run (one rank per GPU)")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    lib = _lib.load()
+    pk, pk_src = peaks()
+    W, Ksteps = args.warmup, args.steps
+    out = {}
+
+    if args.workload in ("both", "score"):
+        n_q = args.users_per_step * world
+        g = torch.Generator(device=device).manual_seed(1)
+        user_tab = torch.randn(args.n_users, D, device=device, generator=g) * 0.125
+        ib, ie = shard_range(args.n_items, rank, world)
+        gi = torch.Generator(device=device).manual_seed(1000 + rank)
+        item_shard = torch.randn(ie - ib, D, device=device, generator=gi) * 0.125
+        plans_d = make_step_plans(W + Ksteps, n_q, args.n_users, args.n_items, 6, device)
+        plans = [EvalPlan.from_arrays(**p) for p in plans_d]
+        scorer = ShardedFullRankScorer(K, ops.SCORE_TF32_CHECKED)
+
+        def step(plan):
+            s, i = scorer.topk(user_tab, item_shard, ib, plan)
+            return s, i, scorer.metrics(i, plan, TOPN, rounded=False)
+
+        for p in plans[:W]:
+            step(p)
+        barrier(world, device)
+        launches0 = lib.cr_launch_count()
+        lib.cr_profile_enable(1)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(device.index) as clk:
+            ev0.record()
+            for p in plans[W:]:
+                _, _, perf = step(p)
+            ev1.record()
+            barrier(world, device)
+        ms = max_over_ranks(ev0.elapsed_time(ev1), device, world)
+        launches = lib.cr_launch_count() - launches0
+        import ctypes
+        tot, cnt = ctypes.c_double(), ctypes.c_int()
+        lib.cr_profile_read(0, ctypes.byref(tot), ctypes.byref(cnt))
+        lib.cr_profile_enable(0)
+        value = n_q * Ksteps / (ms * 1e-3)
+        sweep_ms = tot.value / max(cnt.value, 1)
+        flops = 2.0 * n_q * (ie - ib) * D                       # algorithmic FLOPs of one sweep launch (this rank's shard)
+        tf32_peak = pk["bf16_tflops_sustained"] / 2.0             # TF32 dense = half the bf16 rate; kernel runs inside a long step
+        achieved = flops / (sweep_ms * 1e-3) / 1e12 if sweep_ms > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": "score_sweep_tc_kernel", "achieved": round(achieved, 1), "peak": round(tf32_peak, 1),
+                    "unit": "TFLOP/s", "frac": round(achieved / tf32_peak, 4), "traffic": None,
+                    "peak_source": f"{pk_src} bf16_tflops_sustained/2 (TF32 dense is half the bf16 rate)",
+                    "launch_ms": round(sweep_ms, 3), "launches": cnt.value, "flop_per_launch": flops,
+                    "share_of_step": round(sweep_ms * cnt.value / ms, 4)}
+
+        # end to end through the host-buffer API: H2D of the step's plan from pinned memory, D2H of top-K + metric sums
+        hb = HostBatchEvaluator(scorer, TOPN, n_q, n_q * MASK_PER_USER, n_q * GT_PER_USER, device)
+        host_plans = [hb.pin(p) for p in plans_d[W:]]
+        hb.run(user_tab, item_shard, ib, host_plans[0])
+        barrier(world, device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for hp in host_plans:
+            res = hb.run(user_tab, item_shard, ib, hp)
+        e1.record()
+        barrier(world, device)
+        e2e_ms = max_over_ranks(e0.elapsed_time(e1), device, world)
+        out.update(metric="full-rank users/sec (top-20 over catalog)", value=round(value, 1), unit="users/s", n_gpus=world,
+                   steps=Ksteps, warmup=W, ms_per_step=round(ms / Ksteps, 3), higher_is_better=True, scaling="weak",
+                   vs_baseline=None, dtype="tf32 select + f32 rescore", data="synthetic",
+                   config={"workload": f"C5 full-catalog top-{K} scoring: {args.n_users} users x {args.n_items} items, d={D}, "
+                                       f"{n_q} users/step, ~{MASK_PER_USER} train-masked + {GT_PER_USER} gt items/user, "
+                                       f"Recall/NDCG@{TOPN} on device",
+                           "parallelism": f"item-sharded x{world} + NCCL candidate all-gather" if world > 1 else "single GPU",
+                           "l2": "inputs larger than L2 (item shard %.0f MB); no flush" % ((ie - ib) * D * 4 / 2**20),
+                           "users_per_step": n_q, "n_items": args.n_items, "K": K},
+                   e2e={"value": round(n_q * Ksteps / (e2e_ms * 1e-3), 1), "unit": "users/s", "h2d_bytes_per_step": hb.h2d_bytes,
+                        "d2h_bytes_per_step": hb.d2h_bytes, "ms_per_step": round(e2e_ms / Ksteps, 3)},
+                   gpu_launches=int(launches), roofline=roofline, clocks=clk.summary(),
+                   check={"ndcg@20": perf[1][3], "recall@20": perf[1][2],
+                          "n_refined_last_step": int(scorer.last_n_refined.item()) if scorer.last_n_refined is not None else None})
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_score_baseline(user_tab, item_shard, plans_d[W], args.cpu_sample_users)
+        del item_shard, plans, plans_d, host_plans, hb
+        torch.cuda.empty_cache()
+
+    if args.workload in ("both", "lightgcn"):
+        lg = run_lightgcn(args, device, rank, world, pk, pk_src, lib)
+        if args.workload == "lightgcn":
+            out = lg
+        else:
+            out["lightgcn"] = lg
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def run_lightgcn(args, device, rank, world, pk, pk_src, lib):
+    import ctypes
+    import coldrec_b200 as cr
+    W, Ksteps = args.warmup, args.steps
+    n_users, n_items = args.n_users, args.n_items
+    g = torch.Generator(device=device).manual_seed(5)
+    wu = torch.exp(torch.randn(n_users, device=device, generator=g))                       # lognormal user activity
+    wi = 1.0 / torch.arange(1, n_items + 1, device=device, dtype=torch.float32) ** 0.8     # Zipf(0.8) item popularity
+    wi = wi[torch.randperm(n_items, device=device, generator=g)]
+    eu = torch.multinomial(wu, args.graph_edges, replacement=True, generator=g)
+    ei = torch.multinomial(wi, args.graph_edges, replacement=True, generator=g)
+    G = cr.bipartite_norm_csr(eu, ei, n_users, n_items)
+    del eu, ei, wu, wi
+    N = n_users + n_items
+    b = (6.0 / (N + 64)) ** 0.5
+    E0u = (torch.rand(n_users, D, device=device, generator=g) * 2 - 1) * b
+    E0i = (torch.rand(n_items, D, device=device, generator=g) * 2 - 1) * b
+    if world == 1:
+        G.plan(D)
+        run = lambda: cr.propagate(G, E0u, E0i, LAYERS)
+        nnz_local = G.nnz
+    else:
+        from coldrec_b200.dist import RowPartitionedGraph
+        PG = RowPartitionedGraph(G.rowptr.cpu().numpy(), G.col.cpu().numpy(), G.val.cpu().numpy(), device)
+        PG.local.plan(D)
+        E0 = torch.cat([E0u, E0i])
+        run = lambda: PG.propagate(E0, LAYERS)
+        nnz_local = PG.local.nnz
+    for _ in range(W):
+        run()
+    barrier(world, device)
+    launches0 = lib.cr_launch_count()
+    lib.cr_profile_enable(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(device.index) as clk:
+        ev0.record()
+        for _ in range(Ksteps):
+            res = run()
+        ev1.record()
+        barrier(world, device)
+    ms = max_over_ranks(ev0.elapsed_time(ev1), device, world)
+    tot, cnt = ctypes.c_double(), ctypes.c_int()
+    lib.cr_profile_read(1, ctypes.byref(tot), ctypes.byref(cnt))
+    lib.cr_profile_enable(0)
+    launches = lib.cr_launch_count() - launches0
+    nnz = G.nnz
+    # nnz*(4 idx + 4 val + 4d) + N*4d (write E_k+1) + 2*N*4d (layer-mean RMW) + 8(N+1) rowptr, per layer
+    bytes_layer = nnz * (8 + 4 * D) + 3 * N * 4 * D + 8 * (N + 1)
+    step_gbs = bytes_layer * LAYERS / (ms / Ksteps * 1e-3) / 1e9 / world
+    rows_ms = tot.value / max(cnt.value, 1)
+    out = dict(metric="LightGCN edges/sec (stored nonzeros x layers / s)", value=round(nnz * LAYERS * Ksteps / (ms * 1e-3), 1),
+               unit="edges/s", n_gpus=world, steps=Ksteps, warmup=W, ms_per_step=round(ms / Ksteps, 3), higher_is_better=True,
+               scaling="strong", dtype="f32", data="synthetic",
+               config={"workload": f"C4 LightGCN {LAYERS}-layer propagation: {n_users} users + {n_items} items, {args.graph_edges} "
+                                   f"interactions (nnz(A)={nnz}), d={D}, fused layer mean",
+                       "parallelism": f"row-partitioned x{world} + all-gather per layer" if world > 1 else "single GPU",
+                       "l2": "embedding table %.1f GB >> L2; no flush" % (N * D * 4 / 2**30)},
+               gpu_launches=int(launches),
+               roofline={"bound": "hbm", "kernel": "spmm_rows_kernel (+ long-row split kernels)", "achieved": round(step_gbs, 1),
+                         "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(step_gbs / pk["hbm_gbs"], 4), "traffic": None,
+                         "peak_source": f"{pk_src} hbm_gbs (copy bandwidth)", "bytes_per_layer": bytes_layer,
+                         "rows_kernel_ms": round(rows_ms, 3), "rows_kernel_launches": cnt.value,
+                         "share_of_step": round(tot.value / ms, 4)},
+               clocks=clk.summary())
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_spmm_baseline(G, E0u, E0i)
+    return out
+
+
+# ------------------------------------------------------------------------------------------- CPU arms (oracle port)
+def cpu_score_baseline(user_tab, item_tab, plan_d, n_sample):
+    """The reference's CPU path (oracle restatement of _evaluate + ranking_evaluation) on a bounded sample."""
+    from oracle import coldrec_oracle as O
+    U, I = user_tab.cpu(), item_tab.cpu()
+    uids = plan_d["user_ids"][:n_sample].cpu().numpy()
+    rp = plan_d["mask_rowptr"][:n_sample + 1].cpu().numpy()
+    col = plan_d["mask_col"][:int(rp[-1])].cpu().numpy().astype(np.int64)
+    grp = plan_d["gt_rowptr"][:n_sample + 1].cpu().numpy()
+    gcol = plan_d["gt_col"][:int(grp[-1])].cpu().numpy().astype(np.int64)
+    t0 = time.perf_counter()
+    s, i = O.evaluate_topk_dense_chunked(U, I, uids, rp, col, None, K, user_batch=min(128, n_sample), item_chunk=1 << 20)
+    O.metrics_from_topk(i, grp, gcol, TOPN)
+    dt = time.perf_counter() - t0
+    return {"value": round(n_sample / dt, 2), "unit": "users/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n_sample} users x {I.shape[0]} items (item-chunked torch CPU matmul + mask + topk + metrics), {dt:.1f} s"}
+
+
+def cpu_spmm_baseline(G, E0u, E0i, frac=0.05):
+    """torch.sparse.mm (COO, int64 indices) on the host cores, on a contiguous row sample of the adjacency."""
+    n_rows = int(G.n_rows * frac)
+    lo, hi = 0, int(G.rowptr[n_rows])
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=G.rowptr.device), (G.rowptr[1:n_rows + 1] - G.rowptr[:n_rows]))
+    idx = torch.stack([rows, G.col[lo:hi].long()]).cpu()
+    A = torch.sparse_coo_tensor(idx, G.val[lo:hi].cpu(), (n_rows, G.n_cols)).coalesce()
+    X = torch.cat([E0u, E0i]).cpu()
+    t0 = time.perf_counter()
+    torch.sparse.mm(A, X)
+    dt = time.perf_counter() - t0
+    return {"value": round((hi - lo) / dt, 1), "unit": "edges/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"one layer over the first {n_rows} rows ({hi - lo} nonzeros, {frac:.0%} of rows) of the C4 adjacency, {dt:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port: torch CPU matmul /
+    topk / sparse.mm exactly as ColdRec calls them), all host threads, bounded sample per step."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from oracle import coldrec_oracle as O
+    n_q = args.cpu_sample_users
+    g = torch.Generator().manual_seed(1)
+    U = torch.randn(args.n_users, D, generator=g) * 0.125
+    I = torch.randn(args.n_items, D, generator=g) * 0.125
+    plans = make_step_plans(args.warmup + args.steps, n_q, args.n_users, args.n_items, 6, torch.device("cpu"))
+    def step(p):
+        s, i = O.evaluate_topk_dense_chunked(U, I, p["user_ids"].numpy(), p["mask_rowptr"].numpy(), p["mask_col"].numpy().astype(np.int64),
+                                             None, K, user_batch=min(128, n_q), item_chunk=1 << 20)
+        return O.metrics_from_topk(i, p["gt_rowptr"].numpy(), p["gt_col"].numpy().astype(np.int64), TOPN)
+    for p in plans[:args.warmup]:
+        step(p)
+    t0 = time.perf_counter()
+    for p in plans[args.warmup:]:
+        perf = step(p)
+    dt = time.perf_counter() - t0
+    value = n_q * args.steps / dt
+    cores = torch.get_num_threads()
+    sample = f"{n_q} users/step x {args.n_items} items, item-chunked torch CPU matmul + mask + topk + metrics"
+    print(json.dumps(dict(impl="reference", metric="full-rank users/sec (top-20 over catalog)", value=round(value, 2), unit="users/s",
+                          n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=round(dt / args.steps * 1e3, 1),
+                          higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                          config={"workload": f"C5 full-catalog top-{K} scoring: {args.n_users} users x {args.n_items} items, d={D}; "
+                                              f"CPU sample of {n_q} users/step", "K": K, "n_items": args.n_items},
+                          cpu_baseline={"value": round(value, 2), "unit": "users/s", "cores": cores, "kind": "port", "sample": sample},
+                          e2e={"value": round(value, 2), "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          gpu_launches=0, check={"ndcg@20": perf[1][3]})), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

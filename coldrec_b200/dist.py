@@ -60,15 +60,18 @@ class ShardedFullRankScorer:
     def __init__(self, K: int, precision: int = ops.SCORE_TF32_CHECKED, group=None,
                  local_topk: Optional[Callable] = None, merge: Optional[Callable] = None, metrics: Optional[Callable] = None):
         self.K, self.precision, self.group = int(K), precision, group
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        on = dist.is_available() and dist.is_initialized()
+        self.rank, self.world = (dist.get_rank(group), dist.get_world_size(group)) if on else (0, 1)
+        self.last_n_refined = None
         self._local_topk = local_topk or self._cuda_local_topk
         self._merge = merge or ops.topk_merge
         self._metrics = metrics or (lambda ids, rp, col, Ns: ops.rank_metrics(ids, rp, col, Ns)[0])
 
     def _cuda_local_topk(self, user_tab, item_tab, item_begin, plan: EvalPlan, item_flags):
-        s, i, _ = ops.score_topk(user_tab, item_tab, self.K, user_ids=plan.user_ids, item_id_base=item_begin,
+        s, i, self.last_n_refined = ops.score_topk(user_tab, item_tab, self.K, user_ids=plan.user_ids, item_id_base=item_begin,
                                  mask_rowptr=plan.mask_rowptr, mask_col=plan.mask_col, item_flags=item_flags,
-                                 flag_exclude=plan.flag_exclude if item_flags is not None else 0, precision=self.precision)
+                                                   flag_exclude=plan.flag_exclude if item_flags is not None else 0,
+                                                   precision=self.precision)
         return s, i
 
     def user_slice(self, n_q: int) -> Tuple[int, int]:
@@ -107,7 +110,8 @@ class RowPartitionedGraph:
     def __init__(self, rowptr: np.ndarray, col: np.ndarray, val: Optional[np.ndarray], device, group=None,
                  spmm: Optional[Callable] = None):
         self.group = group
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        on = dist.is_available() and dist.is_initialized()
+        self.rank, self.world = (dist.get_rank(group), dist.get_world_size(group)) if on else (0, 1)
         self.n = len(rowptr) - 1
         self.bounds = partition_rows_by_nnz(np.asarray(rowptr), self.world)
         sizes = np.diff(self.bounds)

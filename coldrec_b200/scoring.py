@@ -157,3 +157,40 @@ class FullRankScorer:
             ops.fill_masked(s, i, n_items_total, item_flags=item_flags if excl else None, flag_exclude=excl,
                             mask_rowptr=plan.mask_rowptr, mask_col=plan.mask_col)
         return s, i
+
+
+class HostBatchEvaluator:
+    """End-to-end evaluation of one eval batch whose plan lives in HOST memory (the shape of the
+    reference's ``_evaluate`` call: users + their train items + ground truth come from Python-side
+    structures, model tables stay on the device): pinned host -> device copies of the plan, fused
+    scoring, device metrics, then device -> host copies of the top-K lists and the metric sums.
+    ``scorer`` is a ``coldrec_b200.dist.ShardedFullRankScorer`` (world size 1 included)."""
+
+    def __init__(self, scorer, Ns: Sequence[int], n_q: int, max_mask_nnz: int, max_gt_nnz: int, device):
+        self.scorer, self.Ns, self.n_q, self.device = scorer, list(Ns), n_q, device
+        e = lambda n, dt: torch.empty(n, dtype=dt, device=device)
+        self.d = dict(user_ids=e(n_q, torch.int32), mask_rowptr=e(n_q + 1, torch.int64), mask_col=e(max_mask_nnz, torch.int32),
+                      gt_rowptr=e(n_q + 1, torch.int64), gt_col=e(max_gt_nnz, torch.int32))
+        lo, hi = scorer.user_slice(n_q) if scorer.world > 1 else (0, n_q)
+        self.out_ids = torch.empty((hi - lo, scorer.K), dtype=torch.int32).pin_memory()
+        self.out_scores = torch.empty((hi - lo, scorer.K), dtype=torch.float32).pin_memory()
+        self.h2d_bytes = 0
+        self.d2h_bytes = (hi - lo) * scorer.K * 8 + len(self.Ns) * 6 * 8
+
+    @staticmethod
+    def pin(plan: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        return {k: v.detach().cpu().pin_memory() for k, v in plan.items()}
+
+    def run(self, user_tab, item_shard, item_begin: int, host_plan: Dict[str, torch.Tensor]):
+        views, nbytes = {}, 0
+        for k, h in host_plan.items():
+            dst = self.d[k][:h.numel()]
+            dst.copy_(h, non_blocking=True)
+            views[k] = dst
+            nbytes += h.numel() * h.element_size()
+        self.h2d_bytes = nbytes
+        plan = EvalPlan.from_arrays(**views)
+        s, i = self.scorer.topk(user_tab, item_shard, item_begin, plan)
+        self.out_ids.copy_(i, non_blocking=True)
+        self.out_scores.copy_(s, non_blocking=True)
+        return self.scorer.metrics(i, plan, self.Ns, rounded=True)     # .cpu() of the sums: the per-step sync
