@@ -7,7 +7,7 @@
 
 Workload (BASELINE.json configs[4] and configs[3], synthetic, seeded):
   scoring   1M users x 10M items, d=64, K=20, ~100 train-masked items and 10 ground-truth items per user.
-            A step = one eval batch of 65,536 x N users against the whole catalogue: fused score + train mask +
+            A step = one eval batch of 75,776 x N users against the whole catalogue: fused score + train mask +
             top-20 + Hit/Precision/Recall/NDCG@{10,20} reduction.  N GPUs shard the catalogue (10M/N items each),
             exchange (score,id) candidates over NCCL and merge; per-GPU work is constant -> weak scaling.
   lightgcn  1M users + 10M items, 100M interactions (nnz(A) ~ 2e8), 3-layer propagation with fused layer mean.
@@ -29,7 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_USERS, N_ITEMS, D, K, TOPN = 1_000_000, 10_000_000, 64, 20, [10, 20]
-USERS_PER_STEP = 65_536
+USERS_PER_STEP = 75_776          # 296 query tiles of 256 = two full waves of 148 SMs
 MASK_PER_USER, GT_PER_USER = 100, 10
 GRAPH_EDGES, LAYERS = 100_000_000, 3
 

@@ -31,8 +31,8 @@ int cr_score_topk_f32(const float* user_tab, const int32_t* user_ids, int64_t n_
     return cr::launch_exact_scorer(job, workspace, ws_bytes, st);
 }
 
-// Probe: raw TF32 scores of the first 256 queries x 128 items as the tensor-core sweep sees them
-// (dbg [256*128] floats).  Test/diagnostic entry point; runs a full cr_score_topk_f32 underneath.
+// Probe: raw TF32 scores of the first 256 queries x 96 items as the tensor-core sweep sees them
+// (dbg [256*96] floats).  Test/diagnostic entry point; runs a full cr_score_topk_f32 underneath.
 int cr_debug_tc_tile(const float* user_tab, int64_t n_q, const float* item_tab, int64_t n_items, int K, float* out_score,
                      int32_t* out_id, float* dbg, void* workspace, size_t ws_bytes, void* stream) {
     if (!user_tab || !item_tab || !out_score || !out_id || !dbg) return CR_ERR_ARG;

@@ -355,9 +355,9 @@ int launch_exact_scorer(const ExactJob& j, void* ws, size_t ws_bytes, cudaStream
 
 // Refinement of the TF32 path: re-run the queries listed on the device (count unknown to the host).
 // Two gated launches cover both regimes without a host sync: a few queries -> 16-way item split with
-// compact partial lists; many queries -> one sweep per 32 queries writing the output rows directly.
+// compact partial lists (a lone CTA sweeping 10M items for one query would be a 40 ms tail); many queries -> one sweep per 32 queries writing the output rows directly.
 constexpr int64_t kRefineSmall = 2048;
-constexpr int kRefineSplits = 16;
+constexpr int kRefineSplits = 128;
 
 size_t refine_workspace_bytes(int K) { return align_up((size_t)kRefineSplits * kRefineSmall * K * 4, 256) * 2; }
 

@@ -1,44 +1,55 @@
-// K1 (tensor-core path) — fused TF32 scorer on tcgen05 with TMA-staged item tiles, TMEM accumulators,
-// an in-epilogue threshold filter, exact fp32 rescoring and a proven-margin check.
+// K1 (tensor-core path) — fused TF32 scorer on tcgen05: query tiles resident in TMEM, TMA-staged item
+// tiles, TMEM accumulators, an in-epilogue threshold filter, exact fp32 rescoring and a proven margin.
 //
 // Replaces MF.batch_predict (model/MF.py:58-63) + mask writes + torch.topk of _evaluate
 // (model/BaseRecommender.py:170-182) for d = 64.  The (B, I) score matrix never exists: scores live
 // only in TMEM and registers.
 //
-// One CTA = one "unit" = 256 queries (two 128-row A tiles, resident in shared memory for the whole
-// sweep) x one contiguous range of item tiles.  Warp roles (384 threads):
-//   warp 0      TMA producer: item tiles (128 items x 64 fp32 = two SWIZZLE_128B boxes) into a 4-stage ring
-//   warp 1      MMA issuer: 16 x tcgen05.mma kind::tf32 (M128 N128 K8) per tile into one of two TMEM stages
-//   warp 2      mask producer: per tile a 128-bit "do not take" bitmap per query (train items via a
-//               monotone cursor in the sorted CSR row, flagged items, items past the end) in shared memory
-//   warp 3      idle (owns the TMEM allocation)
-//   warps 4-11  epilogue: thread = one query (= one TMEM lane).  Per 32-column chunk: tcgen05.ld,
-//               3-input max tree, one compare against the query's running threshold (the KSEL-th best
-//               approximate score).  Only when some lane beats its threshold does the warp enter the
-//               cooperative slow path: the lane's 32 values are transposed through shared memory, each
-//               lane tests one column against threshold and bitmap, survivors are appended to the query's
-//               candidate buffer (global memory, L2 resident); a full buffer is rank-compacted by the warp.
-// After the sweep a second kernel re-scores every candidate in exact fp32 (k = 0..63 in order), selects
-// the top-K by (score desc, id asc) and proves the selection: every rejected item has approximate
-// score <= thr, hence exact score <= thr + eps with eps = 2^-8.9 |q| max|x| (TF32 operand truncation),
-// so the list is exact if its K-th exact score exceeds thr + eps.  Queries that fail the proof are
-// re-run by the exact fp32 scorer (score_simt.cu) in the same call.
+// One CTA = one "unit" = 256 queries x one contiguous range of 96-item tiles.  Warp roles (384 threads):
+//   warp 0      TMA producer: item tiles (96 items x 64 fp32 = two SWIZZLE_128B boxes) into a 6-stage ring
+//   warp 1      MMA issuer: per tile 2 x 8 tcgen05.mma kind::tf32 (M128 N96 K8) with the A operand (queries)
+//               read from TENSOR MEMORY — re-reading A from shared memory for every K=8 slice made the
+//               first version shared-memory-bandwidth bound (ncu r01: tensor pipe 41 % active)
+//   warp 2      mask producer: per tile a 96-bit "do not take" bitmap per query (train items via a monotone
+//               cursor in the sorted CSR row, flagged items, items past the end) in shared memory
+//   warp 3      owns the TMEM allocation
+//   warps 4-11  epilogue: thread = one query = one TMEM lane.  At start each thread stores its own query
+//               vector into TMEM (tcgen05.st) — that is the A operand.  Per 32-column chunk: tcgen05.ld
+//               (software pipelined one chunk ahead), 3-input max tree, one compare against the query's
+//               running threshold (the KSEL-th best approximate score).  Only when some lane beats its
+//               threshold does the warp enter the cooperative slow path: the lane's 32 values are
+//               transposed through shared memory, each lane tests one column against threshold and bitmap,
+//               survivors are appended to the query's candidate buffer (global memory, L2 resident); a
+//               full buffer is rank-compacted by the warp.
+// TMEM columns: [0,128) queries (2 tiles x 64), then 2 accumulator stages x 2 query tiles x 96 columns.
+//
+// After the sweep: rescore_kernel re-scores every candidate in exact fp32 (k = 0..63 in order) and keeps the
+// top-K by (score desc, id asc) per (query, item split); the splits are merged; verify_kernel proves the
+// result: every rejected item has TF32 score <= thr (the largest final threshold over the splits), hence exact
+// score <= thr + eps with eps = 2^-8.9 |q| max|x| (TF32 truncation of both operands), so the list is exact
+// if its K-th exact score exceeds thr + eps.  Queries that fail the proof are re-run by the exact fp32
+// scorer (score_simt.cu) in the same call.
 #include <cuda.h>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int kD = 64;                 // embedding width served by this path
-constexpr int kBM = 256;               // queries per unit (2 x 128-row MMA tiles)
-constexpr int kBN = 128;               // items per tile
-constexpr int kStages = 4;             // item smem ring
-constexpr int kAcc = 2;                // TMEM accumulator stages (2 x 256 columns)
+constexpr int kD = 64;                  // embedding width served by this path
+constexpr int kBM = 256;                // queries per unit (2 x 128-row MMA tiles)
+constexpr int kBN = 96;                 // items per tile
+constexpr int kChunks = kBN / 32;       // 32-column epilogue chunks per tile
+constexpr int kStages = 6;              // item smem ring
+constexpr int kAcc = 2;                 // TMEM accumulator stages
+constexpr int kMaskStages = 4;          // mask-bitmap ring (decoupled from the accumulators: ncu r01b showed the
+                                        // epilogue waiting 40 % of its time on a bitmap tied to the 2 TMEM stages)
 constexpr int kThreads = 384;
-constexpr int kEpiWarp0 = 4;           // first epilogue warp
-constexpr int kChunkBytes = 128 * 128; // one SWIZZLE_128B box: 128 rows x 32 fp32
+constexpr int kEpiWarp0 = 4;            // first epilogue warp
+constexpr int kChunkBytes = kBN * 128;  // one SWIZZLE_128B box: 96 rows x 32 fp32
 constexpr int kTileBytes = 2 * kChunkBytes;
-constexpr float kEpsFactor = 2.1e-3f;  // > 2^-9 * (1 + 2^-10) + fp32 accumulation slack, see header comment
+constexpr int kTmemA = 0;               // query tiles: columns [0, 128)
+constexpr int kTmemAcc = 128;           // accumulators: 128 + a*192 + t*96
+constexpr float kEpsFactor = 2.1e-3f;   // > 2^-9 (1 + 2^-10) + fp32 accumulation slack
 constexpr uint32_t kSpinLimit = 1u << 26;
 
 struct Cand {
@@ -93,37 +104,55 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+// D[tmem] (+)= A[tmem] . B[smem]^T, kind::tf32
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+#define CR_R32(r, o) "=r"(r[o + 0]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]), "=r"(r[o + 6]), "=r"(r[o + 7])
+#define CR_I32(r, o) "r"(r[o + 0]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), "r"(r[o + 6]), "r"(r[o + 7])
+#define CR_LIST32                                                                                                           \
+    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, " \
+    "%26, %27, %28, %29, %30, %31}"
+// issue only; the caller waits with tmem_ld_wait() before touching r[]
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 " CR_LIST32 ", [%32];"
+                 : CR_R32(r, 0), CR_R32(r, 8), CR_R32(r, 16), CR_R32(r, 24)
+                 : "r"(taddr)
+                 : "memory");
 }
+#define CR_RW32(r, o) "+r"(r[o + 0]), "+r"(r[o + 1]), "+r"(r[o + 2]), "+r"(r[o + 3]), "+r"(r[o + 4]), "+r"(r[o + 5]), "+r"(r[o + 6]), "+r"(r[o + 7])
+// wait for the outstanding tcgen05.ld; r[] is an in/out operand so no use of it can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : CR_RW32(r, 0), CR_RW32(r, 8), CR_RW32(r, 16), CR_RW32(r, 24)::"memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], " CR_LIST32 ";" ::CR_I32(r, 0), CR_I32(r, 8), CR_I32(r, 16),
+                 CR_I32(r, 24), "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float max3(float a, float b, float c) {
     float r;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
+}
+// max of 32 registers as a depth-4 tree of 3-input max (17 ALU ops, no long dependency chain)
+__device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
+    float l1[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) l1[i] = max3(__uint_as_float(r[3 * i]), __uint_as_float(r[3 * i + 1]), __uint_as_float(r[3 * i + 2]));
+    l1[10] = fmaxf(__uint_as_float(r[30]), __uint_as_float(r[31]));
+    const float a = max3(l1[0], l1[1], l1[2]), b = max3(l1[3], l1[4], l1[5]), c = max3(l1[6], l1[7], l1[8]);
+    const float d = fmaxf(l1[9], l1[10]);
+    return fmaxf(max3(a, b, c), d);
 }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row groups are
@@ -132,17 +161,18 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
 }
-// kind::tf32 instruction descriptor: D=F32, A=B=TF32, both K-major, N=128, M=128.
+// kind::tf32 instruction descriptor: D=F32, A=B=TF32, both K-major, N=96, M=128.
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 // ---------------------------------------------------------------------------------------------- sweep
 struct SweepParams {
-    int64_t n_q;             // valid queries (rows of Q beyond it are TMA zero fill)
+    const float* Q;          // [n_q, 64] gathered query vectors
+    int64_t n_q;             // valid queries
     int n_q_pad;             // n_utiles * 256
     int n_utiles;
     int64_t n_items;
     int tiles_per_split;
-    int n_tiles;             // ceil(n_items / 128)
+    int n_tiles;             // ceil(n_items / kBN)
     const int32_t* item_gids;
     int64_t item_id_base;
     const int64_t* mask_rowptr;
@@ -152,15 +182,15 @@ struct SweepParams {
     Cand* buf;               // [S][n_q_pad][CAP]
     int* cnt;                // [S][n_q_pad]
     float* thr;              // [S][n_q_pad]
-    float* dbg_scores;       // optional: raw TF32 scores of the first 256 x 128 block (probe)
+    float* dbg_scores;       // optional: raw TF32 scores of the first 256 x 96 block (probe)
 };
 
 struct SmemLayout {
-    static constexpr int kA = 0;                                   // 2 utiles x 2 k-chunks x 16 KB
-    static constexpr int kB = kA + 4 * kChunkBytes;                // kStages x 32 KB
-    static constexpr int kMask = kB + kStages * kTileBytes;        // [kAcc][4 words][256 queries] u32
-    static constexpr int kCommon = kMask + kAcc * 4 * kBM * 4;     // [kAcc][4] u32
-    static constexpr int kScratch = kCommon + 64;                  // 8 warps x 32 floats
+    static constexpr int kB = 0;                                       // kStages x 24 KB
+    static constexpr int kMask = kB + kStages * kTileBytes;            // [kMaskStages][kChunks][256 queries] u32
+    static constexpr int kCommon = kMask + kMaskStages * kChunks * kBM * 4;   // [kMaskStages][kChunks] u32 (padded to 64 B)
+    static constexpr int kDirty = kCommon + 64;                        // [kMaskStages][32 lanes] u32: words a lane must clear
+    static constexpr int kScratch = kDirty + kMaskStages * 32 * 4;     // 8 warps x 32 floats
     static constexpr int kBars = kScratch + 8 * 128;
     static constexpr int kTotal = kBars + 256;
 };
@@ -202,12 +232,10 @@ __device__ float warp_shrink(Cand* buf, int cnt, int ksel, int lane) {
 }
 
 template <int KSEL>
-__global__ void __launch_bounds__(kThreads, 1)
-score_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_i, const SweepParams p) {
+__global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_i, const SweepParams p) {
     constexpr int CAP = KSEL + 32;
     constexpr int EPL = CAP / 32;
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* sA = smem + SmemLayout::kA;
     unsigned char* sB = smem + SmemLayout::kB;
     uint32_t* sMask = reinterpret_cast<uint32_t*>(smem + SmemLayout::kMask);
     uint32_t* sCommon = reinterpret_cast<uint32_t*>(smem + SmemLayout::kCommon);
@@ -216,10 +244,11 @@ score_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     uint64_t* full = bars;                      // [kStages]  TMA -> MMA
     uint64_t* empty = bars + kStages;           // [kStages]  MMA -> TMA
     uint64_t* tfull = bars + 2 * kStages;       // [kAcc]     MMA -> epilogue
-    uint64_t* tempty = tfull + kAcc;            // [kAcc]     epilogue -> MMA / mask producer
-    uint64_t* mfull = tempty + kAcc;            // [kAcc]     mask producer -> epilogue
-    uint64_t* afull = mfull + kAcc;             // [1]        query tiles landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
+    uint64_t* tempty = tfull + kAcc;            // [kAcc]     epilogue -> MMA
+    uint64_t* mfull = tempty + kAcc;            // [kMaskStages] mask producer -> epilogue
+    uint64_t* mempty = mfull + kMaskStages;     // [kMaskStages] epilogue -> mask producer
+    uint64_t* aready = mempty + kMaskStages;    // [1]        query tiles stored in TMEM (8 epilogue warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aready + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int utile = blockIdx.x % p.n_utiles, split = blockIdx.x / p.n_utiles;
@@ -229,8 +258,9 @@ score_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < kAcc; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); mbar_init(&mfull[a], 1); }
-        mbar_init(afull, 1);
+        for (int a = 0; a < kAcc; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+        for (int m = 0; m < kMaskStages; ++m) { mbar_init(&mfull[m], 1); mbar_init(&mempty[m], 8); }
+        mbar_init(aready, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -243,10 +273,6 @@ score_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            mbar_expect_tx(afull, 4 * kChunkBytes);
-            for (int t = 0; t < 2; ++t)
-                for (int kc = 0; kc < 2; ++kc)
-                    tma_load_2d(sA + (t * 2 + kc) * kChunkBytes, &map_q, afull, kc * 32, utile * kBM + t * 128);
             for (int i = 0; i < n_local; ++i) {
                 const int s = i % kStages;
                 if (i >= kStages) mbar_wait(&empty[s], ((i / kStages) - 1) & 1);
@@ -259,7 +285,8 @@ score_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            mbar_wait(afull, 0);
+            mbar_wait(aready, 0);
+            tc_fence_after();
             for (int i = 0; i < n_local; ++i) {
                 const int s = i % kStages, a = i % kAcc;
                 if (i >= kAcc) mbar_wait(&tempty[a], ((i / kAcc) - 1) & 1);
@@ -268,12 +295,12 @@ score_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                 const uint32_t b0 = smem_u32(sB + s * kTileBytes);
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
-                    const uint32_t a0 = smem_u32(sA + t * 2 * kChunkBytes);
-                    const uint32_t dcol = tmem_base + a * 256 + t * 128;
+                    const uint32_t dcol = tmem_base + kTmemAcc + a * (2 * kBN) + t * kBN;
+                    const uint32_t acol = tmem_base + kTmemA + t * kD;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const uint32_t off = (k >> 2) * kChunkBytes + (k & 3) * 32;
-                        umma_tf32(dcol, smem_desc_sw128(a0 + off), smem_desc_sw128(b0 + off), kIdesc, k > 0 ? 1u : 0u);
+                        umma_tf32_ts(dcol, acol + k * 8, smem_desc_sw128(b0 + off), kIdesc, k > 0 ? 1u : 0u);
                     }
                 }
                 umma_commit(&empty[s]);
@@ -283,49 +310,64 @@ score_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     } else if (warp == 2) {
         // ===== mask producer: lane owns queries lane + 32*j, j = 0..7 =====
         int cur[8], endp[8], nxt[8];
-        const int64_t gid_first = p.item_gids ? 0 : p.item_id_base + (int64_t)tile_begin * kBN;
+        int64_t rlo[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int64_t q = (int64_t)utile * kBM + lane + 32 * j;
-            cur[j] = 0; endp[j] = 0; nxt[j] = 0x7fffffff;
+            cur[j] = 0; endp[j] = 0; nxt[j] = 0x7fffffff; rlo[j] = 0;
             if (p.mask_rowptr && q < p.n_q && n_local > 0) {
                 const int64_t lo = p.mask_rowptr[q], hi = p.mask_rowptr[q + 1];
-                // first train item at or after the first global id of this split
-                const int first_gid = p.item_gids ? __ldg(p.item_gids + (int64_t)tile_begin * kBN) : (int)gid_first;
-                int64_t a = lo, b = hi;
+                const int64_t pos_first = (int64_t)tile_begin * kBN;
+                const int first_gid = p.item_gids ? __ldg(p.item_gids + pos_first) : (int)(p.item_id_base + pos_first);
+                int64_t a = lo, b = hi;   // first train item at or after the first global id of this split
                 while (a < b) {
                     const int64_t mid = (a + b) >> 1;
                     if (__ldg(p.mask_col + mid) < first_gid) a = mid + 1; else b = mid;
                 }
-                cur[j] = (int)(a - lo); endp[j] = (int)(hi - lo);
+                rlo[j] = lo; cur[j] = (int)(a - lo); endp[j] = (int)(hi - lo);
                 if (cur[j] < endp[j]) nxt[j] = __ldg(p.mask_col + a);
             }
         }
+        uint32_t* sDirty = reinterpret_cast<uint32_t*>(smem + SmemLayout::kDirty);
+        for (int w = lane; w < kMaskStages * kChunks * kBM; w += 32) sMask[w] = 0;     // bitmaps start clean and are
+        for (int m = 0; m < kMaskStages; ++m) sDirty[m * 32 + lane] = 0;               // cleaned lazily afterwards
+        __syncwarp();
+        const bool plain = !p.item_gids && !p.item_flags;
         for (int i = 0; i < n_local; ++i) {
-            const int a = i % kAcc;
-            if (i >= kAcc) mbar_wait(&tempty[a], ((i / kAcc) - 1) & 1);
-            uint32_t* mk = sMask + a * 4 * kBM;
-            for (int w = lane; w < kBM; w += 32) {   // zero: [4][256] words, 4 KB
-                mk[w] = 0; mk[kBM + w] = 0; mk[2 * kBM + w] = 0; mk[3 * kBM + w] = 0;
-            }
-            const int64_t pos0 = (int64_t)(tile_begin + i) * kBN;
-            // bits common to every query: flagged items and positions past the end of the table
-            int gid_lo = 0, gid_hi = 0;   // global id range covered by this tile: [gid_lo, gid_hi]
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int64_t pos = pos0 + c * 32 + lane;
-                bool bad = pos >= p.n_items;
-                int gid = 0x7fffffff;
-                if (!bad) {
-                    gid = p.item_gids ? __ldg(p.item_gids + pos) : (int)(p.item_id_base + pos);
-                    if (p.item_flags) bad = (__ldg(p.item_flags + gid) & p.flag_exclude) != 0;
+            const int a = i % kMaskStages;
+            if (i >= kMaskStages) mbar_wait(&mempty[a], ((i / kMaskStages) - 1) & 1);
+            uint32_t* mk = sMask + a * kChunks * kBM;
+            {   // clear only the words this lane set the last time the stage was used (bit b -> chunk b%3, query lane+32*(b/3))
+                uint32_t dm = sDirty[a * 32 + lane];
+                while (dm) {
+                    const int b = __ffs(dm) - 1;
+                    dm &= dm - 1;
+                    mk[(b % kChunks) * kBM + lane + 32 * (b / kChunks)] = 0;
                 }
-                const unsigned bits = __ballot_sync(CR_FULL_MASK, bad);
-                if (lane == 0) sCommon[a * 4 + c] = bits;
-                if (c == 0) gid_lo = __shfl_sync(CR_FULL_MASK, gid, 0);
-                // last valid gid of the tile
-                const unsigned valid = __ballot_sync(CR_FULL_MASK, pos < p.n_items);
-                if (valid) gid_hi = __shfl_sync(CR_FULL_MASK, gid, 31 - __clz(valid));
+            }
+            uint32_t dirty = 0;
+            const int64_t pos0 = (int64_t)(tile_begin + i) * kBN;
+            int gid_lo = 0, gid_hi = 0;   // global id range covered by this tile: [gid_lo, gid_hi]
+            if (plain && pos0 + kBN <= p.n_items) {      // common case: contiguous ids, no flags, full tile
+                gid_lo = (int)(p.item_id_base + pos0);
+                gid_hi = gid_lo + kBN - 1;
+                if (lane < kChunks) sCommon[a * kChunks + lane] = 0;
+            } else {
+#pragma unroll
+                for (int c = 0; c < kChunks; ++c) {
+                    const int64_t pos = pos0 + c * 32 + lane;
+                    bool bad = pos >= p.n_items;
+                    int gid = 0x7fffffff;
+                    if (!bad) {
+                        gid = p.item_gids ? __ldg(p.item_gids + pos) : (int)(p.item_id_base + pos);
+                        if (p.item_flags) bad = (__ldg(p.item_flags + gid) & p.flag_exclude) != 0;
+                    }
+                    const unsigned bits = __ballot_sync(CR_FULL_MASK, bad);
+                    if (lane == 0) sCommon[a * kChunks + c] = bits;
+                    if (c == 0) gid_lo = __shfl_sync(CR_FULL_MASK, gid, 0);
+                    const unsigned valid = __ballot_sync(CR_FULL_MASK, pos < p.n_items);
+                    if (valid) gid_hi = __shfl_sync(CR_FULL_MASK, gid, 31 - __clz(valid));
+                }
             }
             __syncwarp();
 #pragma unroll
@@ -342,12 +384,15 @@ score_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                         }
                         if (pos0 + lo2 < p.n_items && __ldg(p.item_gids + pos0 + lo2) == nxt[j]) pos = lo2;
                     }
-                    if (pos >= 0 && pos < kBN) mk[(pos >> 5) * kBM + lane + 32 * j] |= 1u << (pos & 31);
+                    if (pos >= 0 && pos < kBN) {
+                        mk[(pos >> 5) * kBM + lane + 32 * j] |= 1u << (pos & 31);
+                        dirty |= 1u << (j * kChunks + (pos >> 5));
+                    }
                     ++cur[j];
-                    const int64_t q = (int64_t)utile * kBM + lane + 32 * j;
-                    nxt[j] = (cur[j] < endp[j]) ? __ldg(p.mask_col + p.mask_rowptr[q] + cur[j]) : 0x7fffffff;
+                    nxt[j] = (cur[j] < endp[j]) ? __ldg(p.mask_col + rlo[j] + cur[j]) : 0x7fffffff;
                 }
             }
+            sDirty[a * 32 + lane] = dirty;
             __syncwarp();
             if (lane == 0) mbar_arrive(&mfull[a]);
         }
@@ -358,45 +403,65 @@ score_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const int ulocal = t * 128 + quad * 32 + lane;               // query index inside the unit
         const int64_t q = (int64_t)utile * kBM + ulocal;
         const bool valid = q < p.n_q;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        {   // A operand: this thread's query vector -> TMEM lane (quad*32 + lane), columns [t*64, t*64+64)
+            uint32_t r[32];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid) v = __ldg(reinterpret_cast<const float4*>(p.Q + q * kD + h * 32) + k);
+                    r[4 * k] = __float_as_uint(v.x); r[4 * k + 1] = __float_as_uint(v.y);
+                    r[4 * k + 2] = __float_as_uint(v.z); r[4 * k + 3] = __float_as_uint(v.w);
+                }
+                tmem_st32(tmem_base + lane_addr + kTmemA + t * kD + h * 32, r);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(aready);
+        }
         float thr = valid ? -CUDART_INF_F : CUDART_INF_F;
         int cnt = 0;
         Cand* mybuf = p.buf + ((int64_t)split * p.n_q_pad + utile * kBM + ulocal) * CAP;
         float* scratch = sScratch + e * 32;
-        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
 
         for (int i = 0; i < n_local; ++i) {
             const int a = i % kAcc;
             mbar_wait(&tfull[a], (i / kAcc) & 1);
-            mbar_wait(&mfull[a], (i / kAcc) & 1);
+            const int ms = i % kMaskStages;
+            mbar_wait(&mfull[ms], (i / kMaskStages) & 1);
             tc_fence_after();
             const int64_t pos0 = (int64_t)(tile_begin + i) * kBN;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                float v[32];
-                tmem_ld32(tmem_base + lane_addr + a * 256 + t * 128 + c * 32, v);
+            const uint32_t acc_addr = tmem_base + lane_addr + kTmemAcc + a * (2 * kBN) + t * kBN;
+            uint32_t rbuf[2][32];
+            tmem_ld32_issue(acc_addr, rbuf[0]);
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) {
+                uint32_t (&r)[32] = rbuf[c & 1];
+                tmem_ld_wait(r);
+                if (c + 1 < kChunks) tmem_ld32_issue(acc_addr + (c + 1) * 32, rbuf[(c + 1) & 1]);   // next chunk in flight
                 if (p.dbg_scores && blockIdx.x == 0 && i == 0) {
 #pragma unroll
-                    for (int x = 0; x < 32; ++x) p.dbg_scores[ulocal * kBN + c * 32 + x] = v[x];
+                    for (int x = 0; x < 32; ++x) p.dbg_scores[ulocal * kBN + c * 32 + x] = __uint_as_float(r[x]);
                 }
-                float m = max3(v[0], v[1], v[2]);
-#pragma unroll
-                for (int x = 3; x < 31; x += 2) m = max3(m, v[x], v[x + 1]);
-                m = fmaxf(m, v[31]);
+                const float m = max32(r);
                 unsigned ev = __ballot_sync(CR_FULL_MASK, m > thr);
                 while (ev) {
                     const int L = __ffs(ev) - 1;
                     ev &= ev - 1;
                     if (lane == L) {
-                        float4* dst = reinterpret_cast<float4*>(scratch);
+                        uint4* dst = reinterpret_cast<uint4*>(scratch);
 #pragma unroll
-                        for (int x = 0; x < 8; ++x) dst[x] = make_float4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+                        for (int x = 0; x < 8; ++x) dst[x] = make_uint4(r[4 * x], r[4 * x + 1], r[4 * x + 2], r[4 * x + 3]);
                     }
                     __syncwarp();
                     const float x = scratch[lane];
                     float thrL = __shfl_sync(CR_FULL_MASK, thr, L);
                     int cntL = __shfl_sync(CR_FULL_MASK, cnt, L);
                     const int uL = t * 128 + quad * 32 + L;
-                    const uint32_t bad = sMask[a * 4 * kBM + c * kBM + uL] | sCommon[a * 4 + c];
+                    const uint32_t bad = sMask[(ms * kChunks + c) * kBM + uL] | sCommon[ms * kChunks + c];
                     const bool ok = !((bad >> lane) & 1u);
                     bool pass = ok && x > thrL;
                     unsigned pm = __ballot_sync(CR_FULL_MASK, pass);
@@ -420,7 +485,7 @@ score_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[a]);
+            if (lane == 0) { mbar_arrive(&tempty[a]); mbar_arrive(&mempty[ms]); }
         }
         const int64_t o = (int64_t)split * p.n_q_pad + utile * kBM + ulocal;
         p.cnt[o] = valid ? cnt : 0;
@@ -431,21 +496,21 @@ score_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     if (warp == 3) tmem_dealloc(tmem_base, 512);
 }
 
-// ---------------------------------------------------------------------------------------------- rescore
+// ---------------------------------------------------------------------------------------------- rescore / verify
 struct RescoreParams {
-    const float* Q;              // [n_q_pad, 64] gathered queries
+    const float* Q;              // [n_q, 64] gathered queries
     const float* item_tab;
     const int32_t* item_gids; int64_t item_id_base;
-    int64_t n_q; int n_q_pad; int n_splits; int K; int cap; int ksel;
+    int64_t n_q; int n_q_pad; int n_splits; int K; int cap;
     const Cand* buf; const int* cnt; const float* thr;
     const float* item_norm2_max;  // device scalar: max_i |x_i|^2
     float* part_score; int32_t* part_id;   // [S][n_q][K]
-    int32_t* refine_flag;        // [n_q] 0/1
+    const float* out_score;      // merged [n_q][K] (verify)
     int32_t* refine_list; int32_t* refine_count;
 };
 
-// One warp per (query, split): exact fp32 scores of the candidates, top-K by (score desc, gid asc),
-// margin proof.  Candidates are never masked items (the sweep's bitmap dropped those).
+// One warp per (query, split): exact fp32 scores of the candidates, top-K by (score desc, gid asc).
+// Candidates are never masked items (the sweep's bitmap dropped those).
 template <int EPL>
 __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
     const int lane = threadIdx.x & 31;
@@ -455,18 +520,11 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
     const int64_t q = w % p.n_q;
     const int64_t o = (int64_t)split * p.n_q_pad + q;
     const int cnt = min(p.cnt[o], p.cap);
-    const float thr = p.thr[o];
     const Cand* buf = p.buf + o * p.cap;
     const float4* qv = reinterpret_cast<const float4*>(p.Q + q * kD);
 
     float es[EPL];
     int eg[EPL];
-    float qn2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < kD / 4; ++k) {
-        const float4 a = __ldg(qv + k);
-        qn2 = fmaf(a.x, a.x, qn2); qn2 = fmaf(a.y, a.y, qn2); qn2 = fmaf(a.z, a.z, qn2); qn2 = fmaf(a.w, a.w, qn2);
-    }
 #pragma unroll
     for (int i = 0; i < EPL; ++i) {
         const int idx = lane + 32 * i;
@@ -501,23 +559,28 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
     float* os = p.part_score + ((int64_t)split * p.n_q + q) * K;
     int32_t* oi = p.part_id + ((int64_t)split * p.n_q + q) * K;
     for (int k = cnt + lane; k < K; k += 32) { os[k] = -CUDART_INF_F; oi[k] = -1; }
-    float kth = -CUDART_INF_F;
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) {
-        const bool have = lane + 32 * i < cnt;
-        if (have && rank[i] < K) { os[rank[i]] = es[i]; oi[rank[i]] = eg[i]; }
-        const unsigned who = __ballot_sync(CR_FULL_MASK, have && rank[i] == K - 1);
-        if (who) kth = __shfl_sync(CR_FULL_MASK, es[i], __ffs(who) - 1);
+    for (int i = 0; i < EPL; ++i)
+        if (lane + 32 * i < cnt && rank[i] < K) { os[rank[i]] = es[i]; oi[rank[i]] = eg[i]; }
+}
+
+// One thread per query, after the merge: prove the list or queue the query for the exact re-run.
+__global__ void verify_kernel(const RescoreParams p) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= p.n_q) return;
+    float thr = -CUDART_INF_F;
+    for (int s = 0; s < p.n_splits; ++s) thr = fmaxf(thr, p.thr[(int64_t)s * p.n_q_pad + q]);
+    if (thr == -CUDART_INF_F) return;          // nothing was ever rejected by a threshold
+    const float4* qv = reinterpret_cast<const float4*>(p.Q + q * kD);
+    float qn2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kD / 4; ++k) {
+        const float4 a = __ldg(qv + k);
+        qn2 = fmaf(a.x, a.x, qn2); qn2 = fmaf(a.y, a.y, qn2); qn2 = fmaf(a.z, a.z, qn2); qn2 = fmaf(a.w, a.w, qn2);
     }
-    // proof: nothing was ever rejected by threshold (thr still -inf), or the K-th exact score clears thr + eps
-    bool proven = (thr == -CUDART_INF_F);
-    if (!proven && cnt >= K) {
-        const float eps = kEpsFactor * sqrtf(qn2) * sqrtf(*p.item_norm2_max);
-        proven = kth > thr + eps;
-    }
-    if (!proven && lane == 0) {
-        if (atomicExch(p.refine_flag + q, 1) == 0) p.refine_list[atomicAdd(p.refine_count, 1)] = (int32_t)q;
-    }
+    const float eps = kEpsFactor * sqrtf(qn2) * sqrtf(*p.item_norm2_max);
+    const float kth = p.out_score[q * p.K + p.K - 1];      // -inf if the merged list is short
+    if (!(kth > thr + eps)) p.refine_list[atomicAdd(p.refine_count, 1)] = (int32_t)q;
 }
 
 __global__ void item_norm_max_kernel(const float4* __restrict__ item4, int64_t n_items, float* out) {
@@ -587,14 +650,14 @@ int get_encode_fn(EncodeTiledFn* out) {
     return CR_OK;
 }
 
-// rows x 64 fp32, row-major; box = 32 floats x 128 rows, SWIZZLE_128B; out-of-range rows read as zero
+// rows x 64 fp32, row-major; box = 32 floats x kBN rows, SWIZZLE_128B; out-of-range rows read as zero
 int make_map(CUtensorMap* map, const float* base, int64_t rows) {
     EncodeTiledFn enc;
     int rc = get_encode_fn(&enc);
     if (rc != CR_OK) return rc;
     cuuint64_t dims[2] = {(cuuint64_t)kD, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)kD * sizeof(float)};
-    cuuint32_t box[2] = {32, 128};
+    cuuint32_t box[2] = {32, (cuuint32_t)kBN};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -605,7 +668,7 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows) {
 
 struct TcPlan {
     int ksel, cap, n_utiles, n_q_pad, n_tiles, S, tiles_per_split;
-    size_t off_q, off_buf, off_cnt, off_thr, off_norm, off_flag, off_list, off_count, off_ps, off_pi, off_exact, exact_bytes, total;
+    size_t off_q, off_buf, off_cnt, off_thr, off_norm, off_list, off_count, off_ps, off_pi, off_exact, exact_bytes, total;
 };
 
 TcPlan tc_plan(int64_t n_q, int64_t n_items, int K) {
@@ -615,26 +678,27 @@ TcPlan tc_plan(int64_t n_q, int64_t n_items, int K) {
     P.n_utiles = (int)((n_q + kBM - 1) / kBM);
     P.n_q_pad = P.n_utiles * kBM;
     P.n_tiles = (int)((n_items + kBN - 1) / kBN);
-    // split the item range until there are ~8 waves of units, keeping >= 64 tiles per unit
-    int S = 1;
-    const int target = 148 * 8;
-    if (P.n_utiles > 0) S = (target + P.n_utiles - 1) / P.n_utiles;
-    const int max_by_tiles = (P.n_tiles + 63) / 64;
-    if (S > max_by_tiles) S = max_by_tiles;
-    if (S > 32) S = 32;
-    if (S < 1) S = 1;
-    P.tiles_per_split = (P.n_tiles + S - 1) / S;
+    // Item-range splits trade wave balance (units vs 148 SMs) against extra selection work: every split re-learns
+    // its thresholds, so the slow-path count grows ~linearly with S.  Pick the S that minimises rounds x tiles/S x penalty.
+    int best = 1;
+    double best_cost = 1e300;
+    const int max_by_tiles = P.n_tiles / 64 > 0 ? P.n_tiles / 64 : 1;
+    for (int S = 1; S <= 32 && S <= max_by_tiles; ++S) {
+        const double rounds = (double)(((int64_t)P.n_utiles * S + 147) / 148);
+        const double cost = rounds * ((P.n_tiles + S - 1) / S) * (1.0 + 0.04 * (S - 1));
+        if (cost < best_cost * 0.999) { best_cost = cost; best = S; }
+    }
+    P.tiles_per_split = (P.n_tiles + best - 1) / best;
     if (P.tiles_per_split < 1) P.tiles_per_split = 1;
     P.S = (P.n_tiles + P.tiles_per_split - 1) / P.tiles_per_split;
     if (P.S < 1) P.S = 1;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = cr::align_up(off + bytes, 256); return o; };
-    P.off_q = take((size_t)P.n_q_pad * kD * 4);
+    P.off_q = take((size_t)(n_q > 0 ? n_q : 1) * kD * 4);
     P.off_buf = take((size_t)P.S * P.n_q_pad * P.cap * sizeof(Cand));
     P.off_cnt = take((size_t)P.S * P.n_q_pad * 4);
     P.off_thr = take((size_t)P.S * P.n_q_pad * 4);
     P.off_norm = take(256);
-    P.off_flag = take((size_t)(n_q > 0 ? n_q : 1) * 4);
     P.off_list = take((size_t)(n_q > 0 ? n_q : 1) * 4);
     P.off_count = take(256);
     P.off_ps = take((size_t)P.S * n_q * K * 4);
@@ -672,7 +736,6 @@ int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_
     int* cnt = (int*)(base + P.off_cnt);
     float* thr = (float*)(base + P.off_thr);
     float* norm = (float*)(base + P.off_norm);
-    int32_t* rflag = (int32_t*)(base + P.off_flag);
     int32_t* rlist = (int32_t*)(base + P.off_list);
     int32_t* rcount = (int32_t*)(base + P.off_count);
     float* part_s = (P.S > 1) ? (float*)(base + P.off_ps) : j.out_score;
@@ -680,7 +743,6 @@ int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_
     const uint8_t* flags = j.flag_exclude ? j.item_flags : nullptr;
 
     CR_CUDA_TRY(cudaMemsetAsync(norm, 0, 256, st));
-    CR_CUDA_TRY(cudaMemsetAsync(rflag, 0, (size_t)n_q * 4, st));
     CR_CUDA_TRY(cudaMemsetAsync(rcount, 0, 256, st));
     {
         const int64_t total = n_q * (kD / 4);
@@ -689,14 +751,12 @@ int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_
         item_norm_max_kernel<<<148 * 4, 256, 0, st>>>((const float4*)j.item_tab, n_items, norm);
         CR_LAUNCH_CHECK("item_norm_max_kernel");
     }
-    CUtensorMap map_q, map_i;
-    int rc = make_map(&map_q, Q, n_q);
-    if (rc != CR_OK) return rc;
-    rc = make_map(&map_i, j.item_tab, n_items);
+    CUtensorMap map_i;
+    int rc = make_map(&map_i, j.item_tab, n_items);
     if (rc != CR_OK) return rc;
 
     SweepParams sp{};
-    sp.n_q = n_q; sp.n_q_pad = P.n_q_pad; sp.n_utiles = P.n_utiles; sp.n_items = n_items;
+    sp.Q = Q; sp.n_q = n_q; sp.n_q_pad = P.n_q_pad; sp.n_utiles = P.n_utiles; sp.n_items = n_items;
     sp.tiles_per_split = P.tiles_per_split; sp.n_tiles = P.n_tiles; sp.item_gids = j.item_gids; sp.item_id_base = j.item_id_base;
     sp.mask_rowptr = j.mask_rowptr; sp.mask_col = j.mask_col; sp.item_flags = flags;
     sp.flag_exclude = j.flag_exclude; sp.buf = buf; sp.cnt = cnt; sp.thr = thr; sp.dbg_scores = dbg_scores;
@@ -704,16 +764,16 @@ int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_
     prof_start(PROF_SCORE_SWEEP, st);
     if (P.ksel == 32) {
         CR_CUDA_TRY(cudaFuncSetAttribute(score_sweep_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::kTotal));
-        score_sweep_tc_kernel<32><<<grid, kThreads, SmemLayout::kTotal, st>>>(map_q, map_i, sp);
+        score_sweep_tc_kernel<32><<<grid, kThreads, SmemLayout::kTotal, st>>>(map_i, sp);
     } else {
         CR_CUDA_TRY(cudaFuncSetAttribute(score_sweep_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::kTotal));
-        score_sweep_tc_kernel<64><<<grid, kThreads, SmemLayout::kTotal, st>>>(map_q, map_i, sp);
+        score_sweep_tc_kernel<64><<<grid, kThreads, SmemLayout::kTotal, st>>>(map_i, sp);
     }
     CR_LAUNCH_CHECK("score_sweep_tc_kernel");
     prof_stop(PROF_SCORE_SWEEP, st);
 
-    RescoreParams rp{Q, j.item_tab, j.item_gids, j.item_id_base, n_q, P.n_q_pad, P.S, K, P.cap, P.ksel, buf, cnt, thr, norm,
-                     part_s, part_i, rflag, rlist, rcount};
+    RescoreParams rp{Q, j.item_tab, j.item_gids, j.item_id_base, n_q, P.n_q_pad, P.S, K, P.cap, buf, cnt, thr, norm,
+                     part_s, part_i, j.out_score, rlist, rcount};
     const int64_t warps = n_q * P.S;
     const unsigned rgrid = (unsigned)((warps * 32 + 255) / 256);
     if (P.cap == 64) rescore_kernel<2><<<rgrid, 256, 0, st>>>(rp); else rescore_kernel<3><<<rgrid, 256, 0, st>>>(rp);
@@ -722,6 +782,8 @@ int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_
         rc = launch_merge(part_s, part_i, P.S, n_q, K, j.out_score, j.out_id, st, nullptr, 0, 0, -1, INT64_MAX);
         if (rc != CR_OK) return rc;
     }
+    verify_kernel<<<(unsigned)((n_q + 255) / 256), 256, 0, st>>>(rp);
+    CR_LAUNCH_CHECK("verify_kernel");
     // lists shorter than K (fewer than K unmasked items): show masked ids at -1e9 like the reference's top-K
     if (j.mask_rowptr || flags) {
         fill_masked_local_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, st>>>(j.out_score, j.out_id, n_q, K, n_items, j.item_gids,

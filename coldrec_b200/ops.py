@@ -131,14 +131,14 @@ def score_topk(user_tab, item_tab, K: int, *, user_ids=None, item_gids=None, ite
 
 
 def debug_tc_tile(user_tab, item_tab, K: int = 20):
-    """Diagnostic: TF32-checked scoring (d=64, no masks) + raw tensor-core scores of the first 256x128 block."""
+    """Diagnostic: TF32-checked scoring (d=64, no masks) + raw tensor-core scores of the first 256x96 block."""
     lib = _lib.load()
     user_tab = _req(user_tab, torch.float32, "user_tab"); item_tab = _req(item_tab, torch.float32, "item_tab")
     dev = _same_device(user_tab, item_tab)
     n_q, n_items = user_tab.shape[0], item_tab.shape[0]
     out_s = torch.empty((n_q, K), dtype=torch.float32, device=dev)
     out_i = torch.empty((n_q, K), dtype=torch.int32, device=dev)
-    dbg = torch.zeros((256, 128), dtype=torch.float32, device=dev)
+    dbg = torch.zeros((256, 96), dtype=torch.float32, device=dev)
     need = lib.cr_score_topk_workspace_bytes(n_q, n_items, 64, K, SCORE_TF32_CHECKED)
     ws = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):

@@ -109,7 +109,7 @@ CR_API int cr_score_topk_f32(const float *user_tab, const int32_t *user_ids, int
                       int precision, void *workspace, size_t ws_bytes, void *stream);
 
 /* Diagnostic probe of the tcgen05 path: like cr_score_topk_f32 (d = 64, TF32-checked, no masks) and
- * additionally dumps the raw TF32 scores of the first 256 queries x first 128 items into dbg[256*128]. */
+ * additionally dumps the raw TF32 scores of the first 256 queries x first 96 items into dbg[256*96]. */
 CR_API int cr_debug_tc_tile(const float *user_tab, int64_t n_q, const float *item_tab, int64_t n_items, int K,
                             float *out_score, int32_t *out_id, float *dbg, void *workspace, size_t ws_bytes, void *stream);
 

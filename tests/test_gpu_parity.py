@@ -356,8 +356,8 @@ def test_tc_raw_scores_are_tf32_products():
     U = (rng.standard_normal((300, 64)) * 0.3).astype(np.float32)
     I = (rng.standard_normal((1000, 64)) * 0.3).astype(np.float32)
     s, i, dbg = ops.debug_tc_tile(cu(U), cu(I))
-    ref = (U[:256].astype(np.float64) @ I[:128].astype(np.float64).T)
-    bound = 2.0 ** -9 * np.linalg.norm(U[:256], axis=1)[:, None] * np.linalg.norm(I[:128], axis=1)[None, :] + 1e-6
+    ref = (U[:256].astype(np.float64) @ I[:96].astype(np.float64).T)
+    bound = 2.0 ** -9 * np.linalg.norm(U[:256], axis=1)[:, None] * np.linalg.norm(I[:96], axis=1)[None, :] + 1e-6
     err = np.abs(dbg.cpu().numpy() - ref)
     assert (err <= bound).all(), f"max err {err.max()} (bound {bound.max()}); tile is not a TF32 product"
     assert err.max() > 1e-7, "suspiciously exact: is the tensor-core path really running?"
