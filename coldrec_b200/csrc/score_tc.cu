@@ -30,6 +30,7 @@
 // if its K-th exact score exceeds thr + eps.  Queries that fail the proof are re-run by the exact fp32
 // scorer (score_simt.cu) in the same call.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -113,6 +114,11 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -183,6 +189,7 @@ struct SweepParams {
     int* cnt;                // [S][n_q_pad]
     float* thr;              // [S][n_q_pad]
     float* dbg_scores;       // optional: raw TF32 scores of the first 256 x 96 block (probe)
+    int dbg_mode;            // timing experiments only (env CR_TC_DEBUG_MODE): 1 = skip TMEM loads, 2 = skip MMAs, 4 = interleave
 };
 
 struct SmemLayout {
@@ -250,7 +257,8 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
     uint64_t* aready = mempty + kMaskStages;    // [1]        query tiles stored in TMEM (8 epilogue warps)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aready + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(CR_FULL_MASK, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
+    const int lane = threadIdx.x & 31;
     const int utile = blockIdx.x % p.n_utiles, split = blockIdx.x / p.n_utiles;
     const int tile_begin = split * p.tiles_per_split;
     const int tile_end = min(p.n_tiles, tile_begin + p.tiles_per_split);
@@ -283,29 +291,33 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            mbar_wait(aready, 0);
+        // ===== MMA issuer: the whole warp walks the loop (uniform control flow), one elected lane issues =====
+        mbar_wait(aready, 0);
+        tc_fence_after();
+        const bool leader = elect_one();
+        // B descriptor = constant high word | (start address >> 4): per MMA only the low word moves
+        constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+        for (int i = 0; i < n_local; ++i) {
+            const int s = i % kStages, a = i % kAcc;
+            if (i >= kAcc) mbar_wait(&tempty[a], ((i / kAcc) - 1) & 1);
+            mbar_wait(&full[s], (i / kStages) & 1);
             tc_fence_after();
-            for (int i = 0; i < n_local; ++i) {
-                const int s = i % kStages, a = i % kAcc;
-                if (i >= kAcc) mbar_wait(&tempty[a], ((i / kAcc) - 1) & 1);
-                mbar_wait(&full[s], (i / kStages) & 1);
-                tc_fence_after();
-                const uint32_t b0 = smem_u32(sB + s * kTileBytes);
+            if (leader) {
+                const uint32_t dlo = ((smem_u32(sB + s * kTileBytes) >> 4) & 0x3FFF) | (1u << 16);
+                const uint32_t d0 = tmem_base + kTmemAcc + a * (2 * kBN);
+                if (!(p.dbg_mode & 2)) {
 #pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const uint32_t dcol = tmem_base + kTmemAcc + a * (2 * kBN) + t * kBN;
-                    const uint32_t acol = tmem_base + kTmemA + t * kD;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint32_t off = (k >> 2) * kChunkBytes + (k & 3) * 32;
-                        umma_tf32_ts(dcol, acol + k * 8, smem_desc_sw128(b0 + off), kIdesc, k > 0 ? 1u : 0u);
+                    for (int m = 0; m < 16; ++m) {
+                        const int t = m >> 3, k = m & 7;
+                        const uint32_t off16 = ((k >> 2) * kChunkBytes + (k & 3) * 32) >> 4;
+                        const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(dlo + off16);
+                        umma_tf32_ts(d0 + t * kBN, tmem_base + kTmemA + t * kD + k * 8, bdesc, kIdesc, k > 0 ? 1u : 0u);
                     }
                 }
                 umma_commit(&empty[s]);
                 umma_commit(&tfull[a]);
             }
+            __syncwarp();
         }
     } else if (warp == 2) {
         // ===== mask producer: lane owns queries lane + 32*j, j = 0..7 =====
@@ -436,6 +448,12 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
             const int64_t pos0 = (int64_t)(tile_begin + i) * kBN;
             const uint32_t acc_addr = tmem_base + lane_addr + kTmemAcc + a * (2 * kBN) + t * kBN;
             uint32_t rbuf[2][32];
+            if (p.dbg_mode & 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&tempty[a]); mbar_arrive(&mempty[ms]); }
+                continue;
+            }
             tmem_ld32_issue(acc_addr, rbuf[0]);
 #pragma unroll
             for (int c = 0; c < kChunks; ++c) {
@@ -760,6 +778,10 @@ int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_
     sp.tiles_per_split = P.tiles_per_split; sp.n_tiles = P.n_tiles; sp.item_gids = j.item_gids; sp.item_id_base = j.item_id_base;
     sp.mask_rowptr = j.mask_rowptr; sp.mask_col = j.mask_col; sp.item_flags = flags;
     sp.flag_exclude = j.flag_exclude; sp.buf = buf; sp.cnt = cnt; sp.thr = thr; sp.dbg_scores = dbg_scores;
+    {
+        const char* e = getenv("CR_TC_DEBUG_MODE");
+        sp.dbg_mode = e ? atoi(e) : 0;
+    }
     const unsigned grid = (unsigned)(P.n_utiles * P.S);
     prof_start(PROF_SCORE_SWEEP, st);
     if (P.ksel == 32) {

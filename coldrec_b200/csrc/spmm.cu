@@ -159,6 +159,93 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
     }
 }
 
+// Grouped variant (d = 4*LPR*NV with LPR < 32): the 32/LPR lane groups of a warp walk DIFFERENT rows.
+// ncu (profiles/r01) showed the warp-per-row kernel latency bound, not bandwidth bound (DRAM 31 % busy, 20
+// resident warps, long-scoreboard stalls): 80 % of the rows of a bipartite item-side graph have <= 8 nonzeros,
+// and each such row paid the full rowptr -> col -> gather dependency chain for a few hundred bytes.  Here a warp
+// owns 128 consecutive rows: row pointers are fetched 32 rows at a time, column ids / values of the next batch
+// of rows and of the next chunk of the same row are prefetched while the current gathers are in flight, and
+// 32/LPR rows are gathered concurrently, so the chain is paid once per 32 rows instead of once per row.
+template <int LPR, int NV, bool HAS_VAL>
+__global__ void __launch_bounds__(kThreads, 3)
+spmm_rows_grouped_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+                         int64_t n_rows, const float4* __restrict__ X4, float4* __restrict__ Y4, const float4* acc_in4,
+                         float4* acc4, float beta, float div, int long_row) {
+    constexpr int RPW = 32 / LPR;     // rows in flight per warp
+    constexpr int U = 4;              // gathers issued back to back per group
+    constexpr int kRowsPerWarp = 128;
+    constexpr int d4 = LPR * NV;
+    const int lane = threadIdx.x & 31, grp = lane / LPR, sub = lane % LPR;
+    const int64_t row0 = (((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5) * kRowsPerWarp;
+    if (row0 >= n_rows) return;
+    const int64_t row_end = min(n_rows, row0 + kRowsPerWarp);
+    for (int64_t r32 = row0; r32 < row_end; r32 += 32) {
+        const int64_t rr = r32 + lane;
+        int64_t lo = __ldg(rowptr + min(rr, n_rows));
+        int64_t hi = __ldg(rowptr + min(rr + 1, n_rows));
+        const bool skip_row = (rr >= n_rows) || (hi - lo > long_row);   // long rows belong to the split path
+        if (skip_row) hi = lo;
+        int c_nb = 0;
+        float v_nb = 0.f;
+#pragma unroll 1
+        for (int b = 0; b < 32 / RPW; ++b) {
+            const int src = b * RPW + grp;
+            const int64_t s = __shfl_sync(CR_FULL_MASK, lo, src), e = __shfl_sync(CR_FULL_MASK, hi, src);
+            const bool skip = __shfl_sync(CR_FULL_MASK, (int)skip_row, src) != 0;
+            const int64_t row = r32 + src;
+            int c = c_nb;
+            float v = v_nb;
+            if (b == 0) {          // first batch of a 32-row block: nothing was prefetched
+                c = 0; v = 0.f;
+                if (s + sub < e) { c = __ldg(col + s + sub); v = HAS_VAL ? __ldg(val + s + sub) : 1.f; }
+            }
+            if (b + 1 < 32 / RPW) {   // first chunk of the next batch's rows
+                const int64_t s2 = __shfl_sync(CR_FULL_MASK, lo, src + RPW), e2 = __shfl_sync(CR_FULL_MASK, hi, src + RPW);
+                c_nb = 0; v_nb = 0.f;
+                if (s2 + sub < e2) { c_nb = __ldg(col + s2 + sub); v_nb = HAS_VAL ? __ldg(val + s2 + sub) : 1.f; }
+            }
+            const int iters = (int)((e - s + LPR - 1) / LPR);
+            const int max_it = __reduce_max_sync(CR_FULL_MASK, iters);
+            float4 a[NV];
+#pragma unroll
+            for (int nv = 0; nv < NV; ++nv) a[nv] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int it = 0; it < max_it; ++it) {
+                const int64_t base = s + (int64_t)it * LPR;
+                const int64_t nj = base + LPR + sub;      // next chunk of the same row
+                int c_nc = 0;
+                float v_nc = 0.f;
+                if (nj < e) { c_nc = __ldg(col + nj); v_nc = HAS_VAL ? __ldg(val + nj) : 1.f; }
+                const int cnt = (int)max((int64_t)0, min((int64_t)LPR, e - base));
+#pragma unroll
+                for (int t = 0; t < LPR; t += U) {
+                    float4 x[U][NV];
+                    float w[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int cc = __shfl_sync(CR_FULL_MASK, c, grp * LPR + t + u);
+                        const float ww = __shfl_sync(CR_FULL_MASK, v, grp * LPR + t + u);
+                        const bool ok = t + u < cnt;
+                        w[u] = ok ? ww : 0.f;
+                        const float4* px = X4 + (int64_t)cc * d4 + sub;
+#pragma unroll
+                        for (int nv = 0; nv < NV; ++nv) x[u][nv] = ok ? __ldg(px + nv * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int nv = 0; nv < NV; ++nv) fma4(a[nv], w[u], x[u][nv]);
+                }
+                c = c_nc;
+                v = v_nc;
+            }
+            if (!skip && row < n_rows) {
+#pragma unroll
+                for (int nv = 0; nv < NV; ++nv) store_epilogue(Y4, acc_in4, acc4, row * d4 + sub + nv * LPR, a[nv], beta, div);
+            }
+        }
+    }
+}
+
 __global__ void spmm_plan_kernel(const int64_t* __restrict__ rowptr, int64_t n_rows, PlanHeader* hdr, LongRow* long_rows,
                                  Chunk* chunks, int max_long, int max_chunks) {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -229,12 +316,26 @@ struct SpmmArgs {
     cudaStream_t stream;
 };
 
-template <int LPR, int NV, bool BOUNDS>
+template <int LPR, int NV, bool BOUNDS, int GLPR = 0, int GNV = 0>
 int launch_spmm(const SpmmArgs& a) {
     const int long_row = a.hdr ? kLongRow : 0x7fffffff;
     const int64_t blocks = (a.n_rows * 32 + kThreads - 1) / kThreads;
     if (blocks > 0x7fffffffLL) return CR_ERR_UNSUPPORTED;
-    if (a.n_rows > 0) {
+    if constexpr (GLPR > 0) {
+        if (a.n_rows > 0) {
+            const int64_t warps = (a.n_rows + 127) / 128;
+            const unsigned gblocks = (unsigned)((warps * 32 + kThreads - 1) / kThreads);
+            cr::prof_start(cr::PROF_SPMM_ROWS, a.stream);
+            if (a.val)
+                spmm_rows_grouped_kernel<GLPR, GNV, true><<<gblocks, kThreads, 0, a.stream>>>(
+                    a.rowptr, a.col, a.val, a.n_rows, a.X4, a.Y4, a.acc_in4, a.acc4, a.beta, a.div, long_row);
+            else
+                spmm_rows_grouped_kernel<GLPR, GNV, false><<<gblocks, kThreads, 0, a.stream>>>(
+                    a.rowptr, a.col, a.val, a.n_rows, a.X4, a.Y4, a.acc_in4, a.acc4, a.beta, a.div, long_row);
+            CR_LAUNCH_CHECK("spmm_rows_grouped_kernel");
+            cr::prof_stop(cr::PROF_SPMM_ROWS, a.stream);
+        }
+    } else if (a.n_rows > 0) {
         cr::prof_start(cr::PROF_SPMM_ROWS, a.stream);
         if (a.val)
             spmm_rows_kernel<LPR, NV, true, BOUNDS><<<(unsigned)blocks, kThreads, 0, a.stream>>>(
@@ -312,9 +413,9 @@ int cr_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* val,
         a.partial4 = (float4*)(base + L.off_partial);
     }
     switch (d) {
-        case 32: return launch_spmm<8, 1, false>(a);
-        case 64: return launch_spmm<16, 1, false>(a);
-        case 128: return launch_spmm<32, 1, false>(a);
+        case 32: return launch_spmm<8, 1, false, 8, 1>(a);
+        case 64: return launch_spmm<16, 1, false, 8, 2>(a);
+        case 128: return launch_spmm<32, 1, false, 16, 2>(a);
         case 256: return launch_spmm<32, 2, false>(a);
         default:
             if (d <= 128) return launch_spmm<32, 1, true>(a);
