@@ -268,7 +268,8 @@ def run_lightgcn(args, device, rank, world, pk, pk_src, lib):
         nnz_local = G.nnz
     else:
         from coldrec_b200.dist import RowPartitionedGraph
-        PG = RowPartitionedGraph(G.rowptr.cpu().numpy(), G.col.cpu().numpy(), G.val.cpu().numpy(), device)
+        PG = RowPartitionedGraph(G.rowptr.cpu().numpy(), G.col.cpu().numpy(), G.val.cpu().numpy(), device,
+                                 segments=(n_users, n_items))
         PG.local.plan(D)
         E0 = torch.cat([E0u, E0i])
         run = lambda: PG.propagate(E0, LAYERS)

@@ -112,11 +112,15 @@ def _worker(rank, world, port, ret):
 
         G = RowPartitionedGraph(adj.indptr.astype(np.int64), adj.indices.astype(np.int64), adj.data.astype(np.float32), "cpu",
                                 spmm=cpu_spmm)
+        G2 = RowPartitionedGraph(adj.indptr.astype(np.int64), adj.indices.astype(np.int64), adj.data.astype(np.float32), "cpu",
+                                 spmm=cpu_spmm, segments=(c["n_users"], c["n_items"]))
         E0 = torch.cat([Ut, It])
         out = {}
         for ego in (True, False):
             out[ego] = G.propagate(E0, 3, include_ego=ego).numpy()
-        ret[rank] = dict(s=s.numpy(), i=i.numpy(), lo=lo, hi=hi, perf=perf, prop=out, bounds=G.bounds)
+        out["seg"] = G2.propagate(E0, 3).numpy()
+        ret[rank] = dict(s=s.numpy(), i=i.numpy(), lo=lo, hi=hi, perf=perf, prop=out, bounds=G.bounds, parts=G2.parts,
+                         rows_pad=G2.rows_pad)
     finally:
         dist.destroy_process_group()
 
@@ -153,6 +157,13 @@ def test_sharded_scoring_and_partitioned_propagation_world2():
         for r in range(world):
             assert np.abs(ret[r]["prop"][ego] - ref).max() <= 1e-5 * np.abs(ref).max()
     assert ret[0]["bounds"] == ret[1]["bounds"] and ret[0]["bounds"][0] == 0
+    ru, ri = O.propagate(adj, Ut, It, 3)
+    ref = torch.cat([ru, ri]).numpy()
+    for r in range(world):     # two-segment partition: every rank owns a slice of the users and a slice of the items
+        assert np.abs(ret[r]["prop"]["seg"] - ref).max() <= 1e-5 * np.abs(ref).max()
+        (ub, ue), (ib, ie) = ret[r]["parts"][r]
+        assert 0 <= ub < ue <= c["n_users"] <= ib < ie <= c["n_users"] + c["n_items"]
+    assert ret[0]["rows_pad"] <= 0.6 * (c["n_users"] + c["n_items"])
 
 
 def test_partition_helpers():
