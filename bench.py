@@ -101,6 +101,14 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def ncu_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(key)
+    except OSError:
+        return None
+
+
 def make_step_plans(n_steps, n_q, n_users, n_items, seed, device):
     """Per step: eval user ids, train-mask CSR (MASK_PER_USER sorted item ids per user), ground-truth CSR."""
     g = torch.Generator(device=device).manual_seed(seed)
@@ -196,7 +204,8 @@ def run_b200(args):
         tf32_peak = pk["bf16_tflops_sustained"] / 2.0             # TF32 dense = half the bf16 rate; kernel runs inside a long step
         achieved = flops / (sweep_ms * 1e-3) / 1e12 if sweep_ms > 0 else 0.0
         roofline = {"bound": "tensor", "kernel": "score_sweep_tc_kernel", "achieved": round(achieved, 1), "peak": round(tf32_peak, 1),
-                    "unit": "TFLOP/s", "frac": round(achieved / tf32_peak, 4), "traffic": None,
+                    "unit": "TFLOP/s", "frac": round(achieved / tf32_peak, 4),
+                    "traffic": ncu_traffic("score_sweep_tc_kernel_bytes_per_launch") if (world == 1 and n_q == USERS_PER_STEP and args.n_items == N_ITEMS) else None,
                     "peak_source": f"{pk_src} bf16_tflops_sustained/2 (TF32 dense is half the bf16 rate)",
                     "launch_ms": round(sweep_ms, 3), "launches": cnt.value, "flop_per_launch": flops,
                     "share_of_step": round(sweep_ms * cnt.value / ms, 4)}
@@ -305,7 +314,8 @@ def run_lightgcn(args, device, rank, world, pk, pk_src, lib):
                        "l2": "embedding table %.1f GB >> L2; no flush" % (N * D * 4 / 2**30)},
                gpu_launches=int(launches),
                roofline={"bound": "hbm", "kernel": "spmm_rows_kernel (+ long-row split kernels)", "achieved": round(step_gbs, 1),
-                         "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(step_gbs / pk["hbm_gbs"], 4), "traffic": None,
+                         "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(step_gbs / pk["hbm_gbs"], 4),
+                         "traffic": ncu_traffic("spmm_rows_grouped_kernel_bytes_per_launch") if (world == 1 and args.graph_edges == GRAPH_EDGES) else None,
                          "peak_source": f"{pk_src} hbm_gbs (copy bandwidth)", "bytes_per_layer": bytes_layer,
                          "rows_kernel_ms": round(rows_ms, 3), "rows_kernel_launches": cnt.value,
                          "share_of_step": round(tot.value / ms, 4)},

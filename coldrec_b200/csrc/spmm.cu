@@ -114,34 +114,46 @@ __device__ __forceinline__ void reduce_groups(float4 (&a)[NV]) {
         }
 }
 
+// Where a finished row goes: Y and/or the running layer sum, and (multi-GPU) the same row of every peer's
+// gather table — the all-gather of the next layer's input fused into the SpMM epilogue as peer-memory stores.
+struct Epi {
+    float4* Y4; const float4* acc_in4; float4* acc4; float beta, div;
+    float4* const* peers; int n_peers; int64_t peer_off4;   // peers[p][peer_off4 + idx] = y (or the acc result)
+    int peers_get_acc;
+};
+
 // y -> Y and/or acc = (beta*acc_in + y) / div for one float4 of one row (acc_in may alias acc).
-__device__ __forceinline__ void store_epilogue(float4* __restrict__ Y4, const float4* acc_in4, float4* acc4, int64_t idx,
-                                               float4 y, float beta, float div) {
-    if (Y4) Y4[idx] = y;
-    if (acc4) {
+__device__ __forceinline__ void store_epilogue(const Epi& ep, int64_t idx, float4 y) {
+    if (ep.Y4) ep.Y4[idx] = y;
+    if (ep.peers && !ep.peers_get_acc) {
+        for (int p = 0; p < ep.n_peers; ++p) ep.peers[p][ep.peer_off4 + idx] = y;
+    }
+    if (ep.acc4) {
         float4 o = y;
-        if (beta != 0.f) {
-            const float4 p = acc_in4[idx];
-            o.x = fmaf(beta, p.x, y.x);
-            o.y = fmaf(beta, p.y, y.y);
-            o.z = fmaf(beta, p.z, y.z);
-            o.w = fmaf(beta, p.w, y.w);
+        if (ep.beta != 0.f) {
+            const float4 q = ep.acc_in4[idx];
+            o.x = fmaf(ep.beta, q.x, y.x);
+            o.y = fmaf(ep.beta, q.y, y.y);
+            o.z = fmaf(ep.beta, q.z, y.z);
+            o.w = fmaf(ep.beta, q.w, y.w);
         }
-        if (div != 1.f) {
-            o.x = __fdiv_rn(o.x, div);
-            o.y = __fdiv_rn(o.y, div);
-            o.z = __fdiv_rn(o.z, div);
-            o.w = __fdiv_rn(o.w, div);
+        if (ep.div != 1.f) {
+            o.x = __fdiv_rn(o.x, ep.div);
+            o.y = __fdiv_rn(o.y, ep.div);
+            o.z = __fdiv_rn(o.z, ep.div);
+            o.w = __fdiv_rn(o.w, ep.div);
         }
-        acc4[idx] = o;
+        ep.acc4[idx] = o;
+        if (ep.peers && ep.peers_get_acc) {
+            for (int p = 0; p < ep.n_peers; ++p) ep.peers[p][ep.peer_off4 + idx] = o;
+        }
     }
 }
 
 template <int LPR, int NV, bool HAS_VAL, bool BOUNDS>
 __global__ void __launch_bounds__(kThreads)
 spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
-                 int64_t n_rows, const float4* __restrict__ X4, int d4, float4* __restrict__ Y4,
-                 const float4* acc_in4, float4* acc4, float beta, float div, int long_row) {
+                 int64_t n_rows, const float4* __restrict__ X4, int d4, const Epi ep, int long_row) {
     const int64_t row = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
     if (row >= n_rows) return;
     const int lane = threadIdx.x & 31;
@@ -155,7 +167,7 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
     if (lane < LPR) {
 #pragma unroll
         for (int nv = 0; nv < NV; ++nv)
-            if (!BOUNDS || lane + nv * LPR < d4) store_epilogue(Y4, acc_in4, acc4, row * d4 + lane + nv * LPR, a[nv], beta, div);
+            if (!BOUNDS || lane + nv * LPR < d4) store_epilogue(ep, row * d4 + lane + nv * LPR, a[nv]);
     }
 }
 
@@ -169,8 +181,7 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
 template <int LPR, int NV, bool HAS_VAL>
 __global__ void __launch_bounds__(kThreads, 3)
 spmm_rows_grouped_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
-                         int64_t n_rows, const float4* __restrict__ X4, float4* __restrict__ Y4, const float4* acc_in4,
-                         float4* acc4, float beta, float div, int long_row) {
+                         int64_t n_rows, const float4* __restrict__ X4, const Epi ep, int long_row) {
     constexpr int RPW = 32 / LPR;     // rows in flight per warp
     constexpr int U = 4;              // gathers issued back to back per group
     constexpr int kRowsPerWarp = 128;
@@ -240,7 +251,7 @@ spmm_rows_grouped_kernel(const int64_t* __restrict__ rowptr, const int32_t* __re
             }
             if (!skip && row < n_rows) {
 #pragma unroll
-                for (int nv = 0; nv < NV; ++nv) store_epilogue(Y4, acc_in4, acc4, row * d4 + sub + nv * LPR, a[nv], beta, div);
+                for (int nv = 0; nv < NV; ++nv) store_epilogue(ep, row * d4 + sub + nv * LPR, a[nv]);
             }
         }
     }
@@ -291,8 +302,7 @@ spmm_long_chunks_kernel(const PlanHeader* __restrict__ hdr, const Chunk* __restr
 
 __global__ void __launch_bounds__(kThreads)
 spmm_long_reduce_kernel(const PlanHeader* __restrict__ hdr, const LongRow* __restrict__ long_rows,
-                        const float4* __restrict__ partial4, int d4, float4* __restrict__ Y4, const float4* acc_in4,
-                        float4* acc4, float beta, float div) {
+                        const float4* __restrict__ partial4, int d4, const Epi ep) {
     const int lane = threadIdx.x & 31;
     const int n_long = hdr->n_long;
     const int warps = (gridDim.x * kThreads) >> 5;
@@ -304,14 +314,14 @@ spmm_long_reduce_kernel(const PlanHeader* __restrict__ hdr, const LongRow* __res
                 const float4 p = partial4[(int64_t)(lr.chunk_base + c) * d4 + i];
                 sum.x += p.x; sum.y += p.y; sum.z += p.z; sum.w += p.w;
             }
-            store_epilogue(Y4, acc_in4, acc4, (int64_t)lr.row * d4 + i, sum, beta, div);
+            store_epilogue(ep, (int64_t)lr.row * d4 + i, sum);
         }
     }
 }
 
 struct SpmmArgs {
     const int64_t* rowptr; const int32_t* col; const float* val; int64_t n_rows; const float4* X4; int d4;
-    float4* Y4; const float4* acc_in4; float4* acc4; float beta, div;
+    Epi ep;
     PlanHeader* hdr; LongRow* long_rows; Chunk* chunks; float4* partial4;
     cudaStream_t stream;
 };
@@ -328,10 +338,10 @@ int launch_spmm(const SpmmArgs& a) {
             cr::prof_start(cr::PROF_SPMM_ROWS, a.stream);
             if (a.val)
                 spmm_rows_grouped_kernel<GLPR, GNV, true><<<gblocks, kThreads, 0, a.stream>>>(
-                    a.rowptr, a.col, a.val, a.n_rows, a.X4, a.Y4, a.acc_in4, a.acc4, a.beta, a.div, long_row);
+                    a.rowptr, a.col, a.val, a.n_rows, a.X4, a.ep, long_row);
             else
                 spmm_rows_grouped_kernel<GLPR, GNV, false><<<gblocks, kThreads, 0, a.stream>>>(
-                    a.rowptr, a.col, a.val, a.n_rows, a.X4, a.Y4, a.acc_in4, a.acc4, a.beta, a.div, long_row);
+                    a.rowptr, a.col, a.val, a.n_rows, a.X4, a.ep, long_row);
             CR_LAUNCH_CHECK("spmm_rows_grouped_kernel");
             cr::prof_stop(cr::PROF_SPMM_ROWS, a.stream);
         }
@@ -339,10 +349,10 @@ int launch_spmm(const SpmmArgs& a) {
         cr::prof_start(cr::PROF_SPMM_ROWS, a.stream);
         if (a.val)
             spmm_rows_kernel<LPR, NV, true, BOUNDS><<<(unsigned)blocks, kThreads, 0, a.stream>>>(
-                a.rowptr, a.col, a.val, a.n_rows, a.X4, a.d4, a.Y4, a.acc_in4, a.acc4, a.beta, a.div, long_row);
+                a.rowptr, a.col, a.val, a.n_rows, a.X4, a.d4, a.ep, long_row);
         else
             spmm_rows_kernel<LPR, NV, false, BOUNDS><<<(unsigned)blocks, kThreads, 0, a.stream>>>(
-                a.rowptr, a.col, a.val, a.n_rows, a.X4, a.d4, a.Y4, a.acc_in4, a.acc4, a.beta, a.div, long_row);
+                a.rowptr, a.col, a.val, a.n_rows, a.X4, a.d4, a.ep, long_row);
         CR_LAUNCH_CHECK("spmm_rows_kernel");
         cr::prof_stop(cr::PROF_SPMM_ROWS, a.stream);
     }
@@ -355,8 +365,7 @@ int launch_spmm(const SpmmArgs& a) {
             spmm_long_chunks_kernel<LPR, NV, false, BOUNDS><<<grid, kThreads, 0, a.stream>>>(a.hdr, a.chunks, a.col, a.val,
                                                                                              a.X4, a.d4, a.partial4);
         CR_LAUNCH_CHECK("spmm_long_chunks_kernel");
-        spmm_long_reduce_kernel<<<148, kThreads, 0, a.stream>>>(a.hdr, a.long_rows, a.partial4, a.d4, a.Y4, a.acc_in4, a.acc4,
-                                                                a.beta, a.div);
+        spmm_long_reduce_kernel<<<148, kThreads, 0, a.stream>>>(a.hdr, a.long_rows, a.partial4, a.d4, a.ep);
         CR_LAUNCH_CHECK("spmm_long_reduce_kernel");
     }
     return CR_OK;
@@ -392,16 +401,19 @@ int cr_spmm_plan(const int64_t* rowptr, int64_t n_rows, int64_t nnz, int d, void
     return CR_OK;
 }
 
-int cr_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, int64_t nnz,
-                    const float* X, int d, float* Y, const float* acc_in, float* acc, float acc_beta, float acc_div,
-                    void* plan, size_t plan_bytes, void* stream) {
-    if (!rowptr || (!col && nnz > 0) || !X || n_rows < 0 || nnz < 0 || (!Y && !acc) || acc_div == 0.f) return CR_ERR_ARG;
+static int spmm_entry(const int64_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, int64_t nnz, const float* X,
+                      int d, float* Y, const float* acc_in, float* acc, float acc_beta, float acc_div, void* plan,
+                      size_t plan_bytes, float* const* peers, int n_peers, int64_t peer_row_offset, int bcast_acc, void* stream) {
+    if (!rowptr || (!col && nnz > 0) || !X || n_rows < 0 || nnz < 0 || (!Y && !acc && !peers) || acc_div == 0.f) return CR_ERR_ARG;
     if (d <= 0 || d % 4 != 0 || d > 512) return CR_ERR_UNSUPPORTED;
     if (!cr::aligned16(X) || !cr::aligned16(Y) || !cr::aligned16(acc) || !cr::aligned16(acc_in)) return CR_ERR_ALIGN;
     if (acc_in && !acc) return CR_ERR_ARG;
+    if (peers && (n_peers < 1 || peer_row_offset < 0)) return CR_ERR_ARG;
     int rc = cr::require_device();
     if (rc != CR_OK) return rc;
-    SpmmArgs a{rowptr, col, val, n_rows, (const float4*)X, d / 4, (float4*)Y, (const float4*)(acc_in ? acc_in : acc), (float4*)acc, acc_beta, acc_div,
+    SpmmArgs a{rowptr, col, val, n_rows, (const float4*)X, d / 4,
+               Epi{(float4*)Y, (const float4*)(acc_in ? acc_in : acc), (float4*)acc, acc_beta, acc_div, (float4* const*)peers,
+                   peers ? n_peers : 0, peer_row_offset * (d / 4), bcast_acc},
                nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream};
     if (plan) {
         const PlanLayout L = plan_layout(nnz, d);
@@ -422,6 +434,21 @@ int cr_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* val,
             if (d <= 256) return launch_spmm<32, 2, true>(a);
             return launch_spmm<32, 4, true>(a);
     }
+}
+
+int cr_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, int64_t nnz,
+                    const float* X, int d, float* Y, const float* acc_in, float* acc, float acc_beta, float acc_div,
+                    void* plan, size_t plan_bytes, void* stream) {
+    return spmm_entry(rowptr, col, val, n_rows, nnz, X, d, Y, acc_in, acc, acc_beta, acc_div, plan, plan_bytes, nullptr, 0, 0, 0, stream);
+}
+
+int cr_spmm_csr_bcast_f32(const int64_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, int64_t nnz,
+                          const float* X, int d, float* const* peer_tables, int n_peers, int64_t peer_row_offset,
+                          int bcast_acc, const float* acc_in, float* acc, float acc_beta, float acc_div, void* plan,
+                          size_t plan_bytes, void* stream) {
+    if (!peer_tables || (bcast_acc && !acc)) return CR_ERR_ARG;
+    return spmm_entry(rowptr, col, val, n_rows, nnz, X, d, nullptr, acc_in, acc, acc_beta, acc_div, plan, plan_bytes, peer_tables,
+                      n_peers, peer_row_offset, bcast_acc, stream);
 }
 
 }  // extern "C"

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["spmm_plan", "spmm", "score_topk", "topk_merge", "fill_masked", "gather_rows", "rank_metrics", "linear_act", "bn_fold",
+__all__ = ["spmm_plan", "spmm", "spmm_bcast", "score_topk", "topk_merge", "fill_masked", "gather_rows", "rank_metrics", "linear_act", "bn_fold",
            "heater_blend", "SCORE_EXACT_F32", "SCORE_TF32_CHECKED"]
 
 SCORE_EXACT_F32 = _lib.SCORE_EXACT_F32
@@ -87,6 +87,27 @@ def spmm(rowptr, col, val, X, Y=None, acc=None, acc_beta: float = 1.0, acc_div: 
                                  float(acc_beta), float(acc_div), _ptr(plan), 0 if plan is None else plan.numel(), _stream(dev))
     _lib.check(rc, "cr_spmm_csr_f32")
     return Y if Y is not None else acc
+
+
+def spmm_bcast(rowptr, col, val, X, peer_tables_dev: int, n_peers: int, peer_row_offset: int, acc=None, acc_in=None,
+               acc_beta: float = 1.0, acc_div: float = 1.0, plan=None, bcast_acc: bool = False):
+    """SpMM on the local row block whose finished rows are stored straight into every peer's gather table
+    (``peer_tables_dev`` = device address of an array of ``n_peers`` table pointers, e.g. symmetric-memory
+    ``buffer_ptrs_dev``).  The caller barriers the GPUs afterwards."""
+    lib = _lib.load()
+    rowptr = _req(rowptr, torch.int64, "rowptr"); col = _req(col, torch.int32, "col")
+    val = _req(val, torch.float32, "val", optional=True); X = _req(X, torch.float32, "X")
+    acc = _req(acc, torch.float32, "acc", optional=True); acc_in = _req(acc_in, torch.float32, "acc_in", optional=True)
+    dev = _same_device(rowptr, col, val, X, acc, acc_in, plan)
+    n_rows, nnz, d = rowptr.numel() - 1, col.numel(), X.shape[1]
+    if n_rows == 0:
+        return acc
+    with torch.cuda.device(dev):
+        rc = lib.cr_spmm_csr_bcast_f32(_ptr(rowptr), _ptr(col), _ptr(val), n_rows, nnz, _ptr(X), d, ctypes.c_void_p(peer_tables_dev),
+                                       n_peers, peer_row_offset, int(bool(bcast_acc)), _ptr(acc_in), _ptr(acc), float(acc_beta),
+                                       float(acc_div), _ptr(plan), 0 if plan is None else plan.numel(), _stream(dev))
+    _lib.check(rc, "cr_spmm_csr_bcast_f32")
+    return acc
 
 
 # ------------------------------------------------------------------------------------------------ K1
