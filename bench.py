@@ -271,6 +271,7 @@ def run_lightgcn(args, device, rank, world, pk, pk_src, lib):
     b = (6.0 / (N + 64)) ** 0.5
     E0u = (torch.rand(n_users, D, device=device, generator=g) * 2 - 1) * b
     E0i = (torch.rand(n_items, D, device=device, generator=g) * 2 - 1) * b
+    exchange = None
     if world == 1:
         G.plan(D)
         run = lambda: cr.propagate(G, E0u, E0i, LAYERS)
@@ -281,7 +282,14 @@ def run_lightgcn(args, device, rank, world, pk, pk_src, lib):
                                  segments=(n_users, n_items))
         PG.local.plan(D)
         E0 = torch.cat([E0u, E0i])
-        run = lambda: PG.propagate(E0, LAYERS)
+        exchange = "SpMM epilogue peer stores over NVLink (fused all-gather)"
+        try:
+            PG.enable_p2p(D)
+            run = lambda: PG.propagate_p2p(E0, LAYERS)
+            run()
+        except Exception as ex:      # symmetric memory unavailable on this box: NCCL all-gather after each layer
+            exchange = f"NCCL all-gather per layer (peer path unavailable: {type(ex).__name__})"
+            run = lambda: PG.propagate(E0, LAYERS)
         nnz_local = PG.local.nnz
     for _ in range(W):
         run()
@@ -310,7 +318,7 @@ def run_lightgcn(args, device, rank, world, pk, pk_src, lib):
                scaling="strong", dtype="f32", data="synthetic",
                config={"workload": f"C4 LightGCN {LAYERS}-layer propagation: {n_users} users + {n_items} items, {args.graph_edges} "
                                    f"interactions (nnz(A)={nnz}), d={D}, fused layer mean",
-                       "parallelism": f"row-partitioned x{world} + all-gather per layer" if world > 1 else "single GPU",
+                       "parallelism": f"row-partitioned x{world}, {exchange}" if world > 1 else "single GPU",
                        "l2": "embedding table %.1f GB >> L2; no flush" % (N * D * 4 / 2**30)},
                gpu_launches=int(launches),
                roofline={"bound": "hbm", "kernel": "spmm_rows_kernel (+ long-row split kernels)", "achieved": round(step_gbs, 1),

@@ -182,3 +182,46 @@ class RowPartitionedGraph:
                 x = _all_gather_stack(y, self.group).reshape(self.world * self.rows_pad, -1) if self.world > 1 else y
         full = _all_gather_stack(acc, self.group).reshape(self.world * self.rows_pad, -1) if self.world > 1 else acc
         return self.from_padded(full)
+
+    # ---- fused SpMM + all-gather over NVLink peer memory --------------------------------------------------
+    def enable_p2p(self, d: int) -> None:
+        """Allocate three symmetric (peer-mapped) padded tables [W*rows_pad, d]: two ping-pong gather sources and
+        one for the finished layer mean.  Uses torch symmetric memory only as the allocator / pointer exchange /
+        inter-GPU barrier; the data movement is done by the SpMM kernel's own epilogue stores."""
+        import torch.distributed._symmetric_memory as symm_mem
+        dev = self.local.rowptr.device
+        group = self.group if self.group is not None else dist.group.WORLD
+        self._p2p_d, self._xbuf, self._xhdl = d, [], []
+        for _ in range(3):
+            t = symm_mem.empty((self.world * self.rows_pad, d), dtype=torch.float32, device=dev)
+            self._xhdl.append(symm_mem.rendezvous(t, group=group))
+            self._xbuf.append(t)
+
+    def propagate_p2p(self, E0: torch.Tensor, n_layers: int, include_ego: bool = True, padded_io: bool = False) -> torch.Tensor:
+        """Same result as ``propagate``, but every finished row is stored by the SpMM epilogue straight into the
+        gather table of all GPUs (``cr_spmm_csr_bcast_f32``): the per-layer all-gather overlaps the SpMM instead of
+        following it, and the final layer mean is broadcast the same way.  With ``padded_io`` E0 and the result are
+        in the padded node numbering (``to_padded`` / ``from_padded``), which an integrated pipeline keeps resident."""
+        if getattr(self, "_p2p_d", None) != E0.shape[1]:
+            self.enable_p2p(E0.shape[1])
+        W, r0 = self.world, self.rank * self.rows_pad
+        src, hdl = self._xbuf, self._xhdl
+        if padded_io:
+            src[0].copy_(E0)
+        else:
+            src[0].zero_()
+            src[0][self._padded_idx] = E0
+        hdl[0].barrier()                     # nobody still reads the buffers of a previous call
+        count = n_layers + (1 if include_ego else 0)
+        acc = torch.empty((self.rows_pad, E0.shape[1]), dtype=E0.dtype, device=E0.device)
+        plan = self.local.plan(E0.shape[1])
+        for k in range(1, n_layers + 1):
+            last, first = k == n_layers, k == 1
+            x = src[(k - 1) % 2]
+            out_h = hdl[2] if last else hdl[k % 2]
+            ops.spmm_bcast(self.local.rowptr, self.local.col, self.local.val, x, out_h.buffer_ptrs_dev, W, r0, acc=acc,
+                           acc_in=(x[r0:r0 + self.rows_pad] if (first and include_ego) else None),
+                           acc_beta=(0.0 if (first and not include_ego) else 1.0), acc_div=(float(count) if last else 1.0),
+                           plan=plan, bcast_acc=last)
+            out_h.barrier()                  # every GPU's rows have landed everywhere
+        return src[2] if padded_io else self.from_padded(src[2])

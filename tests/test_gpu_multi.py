@@ -1,0 +1,99 @@
+"""2-GPU tests (run with `gpurun --gpus 2`; skipped on a single-GPU box): NCCL item-sharded scoring and the fused
+SpMM + peer-store all-gather must reproduce the single-GPU results."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import coldrec_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _case():
+    rng = np.random.default_rng(77)
+    n_users, n_items, n_q = 3000, 40000, 1500
+    U = (rng.standard_normal((n_users, 64)) * 0.125).astype(np.float32)
+    I = (rng.standard_normal((n_items, 64)) * 0.125).astype(np.float32)
+    uids = rng.choice(n_users, n_q, replace=False).astype(np.int32)
+    rows = [np.sort(rng.choice(n_items, int(rng.integers(0, 80)), replace=False)) for _ in range(n_q)]
+    rowptr = np.zeros(n_q + 1, dtype=np.int64); np.cumsum([len(r) for r in rows], out=rowptr[1:])
+    col = np.concatenate(rows).astype(np.int32)
+    gt = [np.sort(rng.choice(n_items, 6, replace=False)) for _ in range(n_q)]
+    gt_rowptr = np.arange(0, 6 * n_q + 1, 6, dtype=np.int64)
+    gt_col = np.concatenate(gt).astype(np.int32)
+    eu, ei = rng.integers(0, n_users, 200000), rng.integers(0, n_items, 200000)
+    ei[:3000] = 7                       # one long row (> 512 nonzeros) so the split path crosses the partition too
+    return dict(U=U, I=I, uids=uids, rowptr=rowptr, col=col, gt_rowptr=gt_rowptr, gt_col=gt_col, eu=eu, ei=ei,
+                n_users=n_users, n_items=n_items)
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from coldrec_b200 import ops
+        from coldrec_b200.dist import RowPartitionedGraph, ShardedFullRankScorer, shard_range
+        from coldrec_b200.scoring import EvalPlan
+        c = _case()
+        t = lambda a: torch.from_numpy(a).to(dev)
+        plan = EvalPlan.from_arrays(t(c["uids"]), t(c["rowptr"]), t(c["col"]), t(c["gt_rowptr"]), t(c["gt_col"]))
+        sc = ShardedFullRankScorer(20, ops.SCORE_TF32_CHECKED)
+        b, e = shard_range(c["n_items"], rank, world)
+        s, i = sc.topk(t(c["U"]), t(c["I"][b:e].copy()), b, plan)
+        perf = sc.metrics(i, plan, [10, 20], rounded=False)
+        lo, hi = sc.user_slice(plan.n_q)
+        adj = O.normalize_graph_mat(O.bipartite_adjacency(c["eu"], c["ei"], c["n_users"], c["n_items"])).tocsr()
+        adj.sort_indices()
+        G = RowPartitionedGraph(adj.indptr.astype(np.int64), adj.indices.astype(np.int64), adj.data.astype(np.float32), dev,
+                                segments=(c["n_users"], c["n_items"]))
+        E0 = torch.cat([t(c["U"]), t(c["I"])])
+        out_nccl = G.propagate(E0, 3).cpu().numpy()
+        out_p2p = G.propagate_p2p(E0, 3).cpu().numpy()
+        out_p2p_b = G.propagate_p2p(E0, 2, include_ego=False).cpu().numpy()     # buffers reused across calls
+        ret[rank] = dict(s=s.cpu().numpy(), i=i.cpu().numpy(), lo=lo, hi=hi, perf=perf, nccl=out_nccl, p2p=out_p2p, p2p_b=out_p2p_b)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_gpu_sharded_scoring_and_fused_allgather_propagation():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    from coldrec_b200 import ops
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    c = _case()
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    s1, i1, _ = ops.score_topk(t(c["U"]), t(c["I"]), 20, user_ids=t(c["uids"]), mask_rowptr=t(c["rowptr"]), mask_col=t(c["col"]),
+                               precision=ops.SCORE_EXACT_F32)
+    s1, i1 = s1.cpu().numpy(), i1.cpu().numpy()
+    for r in range(world):
+        lo, hi = ret[r]["lo"], ret[r]["hi"]
+        assert np.array_equal(ret[r]["i"], i1[lo:hi]), "2-GPU ids must equal the single-GPU sweep bit for bit"
+        assert np.allclose(ret[r]["s"], s1[lo:hi], atol=1e-6)
+    want = O.metrics_from_topk(i1.astype(np.int64), c["gt_rowptr"], c["gt_col"].astype(np.int64), [10, 20])
+    assert np.allclose(ret[0]["perf"], want, atol=1e-9) and np.allclose(ret[1]["perf"], want, atol=1e-9)
+    adj = O.normalize_graph_mat(O.bipartite_adjacency(c["eu"], c["ei"], c["n_users"], c["n_items"]))
+    Ut, It = torch.from_numpy(c["U"]), torch.from_numpy(c["I"])
+    ref = torch.cat(O.propagate(adj, Ut, It, 3)).numpy()
+    ref_b = torch.cat(O.propagate(adj, Ut, It, 2, include_ego=False)).numpy()
+    for r in range(world):
+        for k, want_k in (("nccl", ref), ("p2p", ref), ("p2p_b", ref_b)):
+            err = np.abs(ret[r][k] - want_k).max()
+            assert err <= 1e-5 * np.abs(want_k).max(), f"rank {r} {k}: {err}"
+    assert np.array_equal(ret[0]["p2p"], ret[1]["p2p"])
