@@ -267,6 +267,18 @@ def run_lightgcn(args, device, rank, world, pk, pk_src, lib):
     ei = torch.multinomial(wi, args.graph_edges, replacement=True, generator=g)
     G = cr.bipartite_norm_csr(eu, ei, n_users, n_items)
     del eu, ei, wu, wi
+    if world > 1:      # multinomial sampling is not bit-reproducible across devices: every rank takes rank 0's graph
+        import torch.distributed as dist
+        nnz_t = torch.tensor([G.nnz], dtype=torch.int64, device=device)
+        dist.broadcast(nnz_t, 0)
+        n0 = int(nnz_t.item())
+        rp = G.rowptr if rank == 0 else torch.empty(n_users + n_items + 1, dtype=torch.int64, device=device)
+        col = G.col if rank == 0 else torch.empty(n0, dtype=torch.int32, device=device)
+        val = G.val if rank == 0 else torch.empty(n0, dtype=torch.float32, device=device)
+        for t_ in (rp, col, val):
+            dist.broadcast(t_, 0)
+        G = cr.CsrGraph(rp, col, val, n_users + n_items)
+        torch.manual_seed(5)
     N = n_users + n_items
     b = (6.0 / (N + 64)) ** 0.5
     E0u = (torch.rand(n_users, D, device=device, generator=g) * 2 - 1) * b
@@ -288,7 +300,8 @@ def run_lightgcn(args, device, rank, world, pk, pk_src, lib):
             run = lambda: PG.propagate_p2p(E0, LAYERS)
             run()
         except Exception as ex:      # symmetric memory unavailable on this box: NCCL all-gather after each layer
-            exchange = f"NCCL all-gather per layer (peer path unavailable: {type(ex).__name__})"
+            print(f"[bench] peer-store path failed on rank {rank}: {type(ex).__name__}: {ex}", file=sys.stderr, flush=True)
+            exchange = f"NCCL all-gather per layer (peer path unavailable: {type(ex).__name__}: {str(ex)[:80]})"
             run = lambda: PG.propagate(E0, LAYERS)
         nnz_local = PG.local.nnz
     for _ in range(W):

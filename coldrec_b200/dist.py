@@ -209,8 +209,7 @@ class RowPartitionedGraph:
         if padded_io:
             src[0].copy_(E0)
         else:
-            src[0].zero_()
-            src[0][self._padded_idx] = E0
+            src[0][self._padded_idx] = E0      # padding rows are never referenced by a column id: no need to clear them
         hdl[0].barrier()                     # nobody still reads the buffers of a previous call
         count = n_layers + (1 if include_ego else 0)
         acc = torch.empty((self.rows_pad, E0.shape[1]), dtype=E0.dtype, device=E0.device)
