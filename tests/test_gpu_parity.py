@@ -292,6 +292,28 @@ def test_score_topk_vs_oracle_synthetic(shape, precision):
         assert (np.diff(si, axis=1) <= 0).all(), "scores must be sorted descending"
 
 
+def test_score_topk_seed_phase_long_sweep_vs_oracle():
+    """A sweep long enough (>= 512 tiles per unit, one item split) to run the threshold seed phase of the tcgen05
+    scorer: 37,888 queries x 60,000 items, ~50 masked items per query, 1 % duplicated item rows (exact ties)."""
+    from coldrec_b200 import ops
+    n_users, n_items, n_q = 40000, 60000, 37888
+    U, I, uids, rowptr, col, flags = _synthetic_scoring_case(4242, n_users, n_items, n_q, 64, 100, 0.01)
+    for excl in (0, 2):
+        col_mask = None if excl == 0 else np.nonzero(flags & excl)[0]
+        ref_s, ref_i = O.evaluate_topk_dense(O.score_mf(t(U), t(I)), uids, rowptr, col.astype(np.int64), col_mask, 20, 2048)
+        s, i, nref = ops.score_topk(cu(U), cu(I), 20, user_ids=cu(uids), mask_rowptr=cu(rowptr), mask_col=cu(col),
+                                    item_flags=cu(flags) if excl else None, flag_exclude=excl, precision=ops.SCORE_TF32_CHECKED)
+        Ut, It = t(U), t(I)
+        cm = set() if col_mask is None else set(col_mask.tolist())
+
+        def exact(j, ids):
+            masked = set(col[rowptr[j]:rowptr[j + 1]].tolist())
+            row = (Ut[uids[j]] @ It.T).numpy()
+            return [O.MASK_SENTINEL if (int(x) in masked or int(x) in cm) else float(row[int(x)]) for x in ids]
+        O.check_topk_parity(ref_s, ref_i, s.cpu().numpy(), i.cpu().numpy().astype(np.int64), exact)
+        assert int(nref.item()) < n_q // 100, "the TF32 margin proof should hold for almost every query"
+
+
 def test_topk_merge_and_item_sharding_equals_single_sweep():
     """Item-sharded scoring + merge (what each GPU does before/after the candidate allgather) must give
     the single-sweep lists bit for bit (ids) — the comparator (score desc, id asc) is order independent."""
