@@ -6,14 +6,14 @@
 // only in TMEM and registers.
 //
 // One CTA = one "unit" = 256 queries x one contiguous range of 96-item tiles.  Warp roles (384 threads):
-//   warp 8      TMA producer: item tiles (96 items x 64 fp32 = two SWIZZLE_128B boxes) into a 6-stage ring
-//   warp 9      MMA issuer: per tile 2 x 8 tcgen05.mma kind::tf32 (M128 N96 K8) with the A operand (queries)
+//   warp 0      TMA producer: item tiles (96 items x 64 fp32 = two SWIZZLE_128B boxes) into a 6-stage ring
+//   warp 1      MMA issuer: per tile 2 x 8 tcgen05.mma kind::tf32 (M128 N96 K8) with the A operand (queries)
 //               read from TENSOR MEMORY — re-reading A from shared memory for every K=8 slice made the
 //               first version shared-memory-bandwidth bound (ncu r01: tensor pipe 41 % active)
-//   warp 10     mask producer: per tile a 96-bit "do not take" bitmap per query (train items via a monotone
+//   warp 2      mask producer: per tile a 96-bit "do not take" bitmap per query (train items via a monotone
 //               cursor in the sorted CSR row, flagged items, items past the end) in shared memory
-//   warp 11     owns the TMEM allocation
-//   warps 0-7   epilogue: thread = one query = one TMEM lane.  At start each thread stores its own query
+//   warp 3      owns the TMEM allocation
+//   warps 4-11  epilogue: thread = one query = one TMEM lane.  At start each thread stores its own query
 //               vector into TMEM (tcgen05.st) — that is the A operand.  Per 32-column chunk: tcgen05.ld
 //               (software pipelined one chunk ahead), 3-input max tree, one compare against the query's
 //               running threshold (the KSEL-th best approximate score).  Only when some lane beats its
@@ -45,11 +45,7 @@ constexpr int kAcc = 2;                 // TMEM accumulator stages
 constexpr int kMaskStages = 4;          // mask-bitmap ring (decoupled from the accumulators: ncu r01b showed the
                                         // epilogue waiting 40 % of its time on a bitmap tied to the 2 TMEM stages)
 constexpr int kThreads = 384;
-// Warp roles.  The single-lane producers sit on the HIGHEST warp ids: the SM's warp arbiter prefers higher ids, and
-// epilogue warps spinning on an mbarrier would otherwise starve the TMA / MMA / mask issuers of issue slots
-// (ncu r01c: with producers on warps 0-2 the epilogue waited 19 % of its time on a bitmap the producer had no slots to build).
-constexpr int kEpiWarps = 8;            // warps 0..7: epilogue (warp % 4 = TMEM lane quadrant, warp / 4 = query tile)
-constexpr int kWarpTma = 8, kWarpMma = 9, kWarpMask = 10, kWarpAlloc = 11;
+constexpr int kEpiWarp0 = 4;            // first epilogue warp
 constexpr int kChunkBytes = kBN * 128;  // one SWIZZLE_128B box: 96 rows x 32 fp32
 constexpr int kTileBytes = 2 * kChunkBytes;
 constexpr int kTmemA = 0;               // query tiles: columns [0, 128)
@@ -79,18 +75,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// non-blocking probe of a phase
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
@@ -205,7 +189,6 @@ struct SweepParams {
     int* cnt;                // [S][n_q_pad]
     float* thr;              // [S][n_q_pad]
     float* dbg_scores;       // optional: raw TF32 scores of the first 256 x 96 block (probe)
-    int seed_tiles;          // threshold seed phase: the first seed_tiles tiles are swept twice (see kernel comment)
     int dbg_mode;            // timing experiments only (env CR_TC_DEBUG_MODE): 1 = skip TMEM loads, 2 = skip MMAs, 4 = interleave
 };
 
@@ -267,9 +250,9 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SmemLayout::kBars);
     uint64_t* full = bars;                      // [kStages]  TMA -> MMA
     uint64_t* empty = bars + kStages;           // [kStages]  MMA -> TMA
-    uint64_t* tfull = bars + 2 * kStages;       // [kAcc][2]  MMA -> the 4 epilogue warps of one query tile
-    uint64_t* tempty = tfull + 2 * kAcc;        // [kAcc][2]  those 4 warps -> MMA (per query tile: a slow warp only holds back its own half)
-    uint64_t* mfull = tempty + 2 * kAcc;            // [kMaskStages] mask producer -> MMA issuer (tfull then implies the bitmap)
+    uint64_t* tfull = bars + 2 * kStages;       // [kAcc]     MMA -> epilogue
+    uint64_t* tempty = tfull + kAcc;            // [kAcc]     epilogue -> MMA
+    uint64_t* mfull = tempty + kAcc;            // [kMaskStages] mask producer -> epilogue
     uint64_t* mempty = mfull + kMaskStages;     // [kMaskStages] epilogue -> mask producer
     uint64_t* aready = mempty + kMaskStages;    // [1]        query tiles stored in TMEM (8 epilogue warps)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aready + 1);
@@ -280,106 +263,89 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
     const int tile_begin = split * p.tiles_per_split;
     const int tile_end = min(p.n_tiles, tile_begin + p.tiles_per_split);
     const int n_local = tile_end - tile_begin;
-    // Threshold seed phase.  A query's threshold starts at -inf, so the first few thousand items of every sweep flood
-    // the slow path (half of all slow-path events fall in the first 1 % of a 1.25M-item sweep and the MMA pipe stalls
-    // behind them).  Instead the first T0 tiles are swept once in "seed mode": the epilogue only records each query's
-    // maximum unmasked score per tile; the KSEL-th largest of those T0 tile maxima is a valid lower bound of the query's
-    // KSEL-th best score (T0 distinct items reach it), so the real sweep — which starts over at tile 0 — begins with a
-    // threshold that is already tight.  Virtual tile v maps to tile v (seed, v < T0) or v - T0 (sweep).
-    const int T0 = (p.seed_tiles > 0 && n_local >= 4 * p.seed_tiles) ? p.seed_tiles : 0;
-    const int n_virtual = n_local + T0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2 * kAcc; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < kAcc; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         for (int m = 0; m < kMaskStages; ++m) { mbar_init(&mfull[m], 1); mbar_init(&mempty[m], 8); }
         mbar_init(aready, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == kWarpAlloc) tmem_alloc(tmem_slot, 512);
+    if (warp == 3) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == kWarpTma) {
+    if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int i = 0; i < n_virtual; ++i) {
+            for (int i = 0; i < n_local; ++i) {
                 const int s = i % kStages;
                 if (i >= kStages) mbar_wait(&empty[s], ((i / kStages) - 1) & 1);
                 mbar_expect_tx(&full[s], kTileBytes);
-                const int row = (tile_begin + (i < T0 ? i : i - T0)) * kBN;
+                const int row = (tile_begin + i) * kBN;
                 tma_load_2d(sB + s * kTileBytes, &map_i, &full[s], 0, row);
                 tma_load_2d(sB + s * kTileBytes + kChunkBytes, &map_i, &full[s], 32, row);
             }
         }
-    } else if (warp == kWarpMma) {
+    } else if (warp == 1) {
         // ===== MMA issuer: the whole warp walks the loop (uniform control flow), one elected lane issues =====
         mbar_wait(aready, 0);
         tc_fence_after();
         const bool leader = elect_one();
         // B descriptor = constant high word | (start address >> 4): per MMA only the low word moves
         constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
-        for (int i = 0; i < n_virtual; ++i) {
+        for (int i = 0; i < n_local; ++i) {
             const int s = i % kStages, a = i % kAcc;
+            if (i >= kAcc) mbar_wait(&tempty[a], ((i / kAcc) - 1) & 1);
             mbar_wait(&full[s], (i / kStages) & 1);
-            // the accumulator is only handed to the epilogue once the tile's mask bitmap exists: the epilogue then
-            // needs a single barrier wait per tile (tfull) and cannot run ahead of the bitmap ring
-            mbar_wait(&mfull[i % kMaskStages], (i / kMaskStages) & 1);
-            const uint32_t dlo = ((smem_u32(sB + s * kTileBytes) >> 4) & 0x3FFF) | (1u << 16);
-            const uint32_t d0 = tmem_base + kTmemAcc + a * (2 * kBN);
+            tc_fence_after();
+            if (leader) {
+                const uint32_t dlo = ((smem_u32(sB + s * kTileBytes) >> 4) & 0x3FFF) | (1u << 16);
+                const uint32_t d0 = tmem_base + kTmemAcc + a * (2 * kBN);
+                if (!(p.dbg_mode & 2)) {
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                if (i >= kAcc) mbar_wait(&tempty[a * 2 + t], ((i / kAcc) - 1) & 1);
-                tc_fence_after();
-                if (leader) {
-                    if (!(p.dbg_mode & 2)) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const uint32_t off16 = ((k >> 2) * kChunkBytes + (k & 3) * 32) >> 4;
-                            const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(dlo + off16);
-                            umma_tf32_ts(d0 + t * kBN, tmem_base + kTmemA + t * kD + k * 8, bdesc, kIdesc, k > 0 ? 1u : 0u);
-                        }
+                    for (int m = 0; m < 16; ++m) {
+                        const int t = m >> 3, k = m & 7;
+                        const uint32_t off16 = ((k >> 2) * kChunkBytes + (k & 3) * 32) >> 4;
+                        const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(dlo + off16);
+                        umma_tf32_ts(d0 + t * kBN, tmem_base + kTmemA + t * kD + k * 8, bdesc, kIdesc, k > 0 ? 1u : 0u);
                     }
-                    if (t == 1) umma_commit(&empty[s]);
-                    umma_commit(&tfull[a * 2 + t]);
                 }
-                __syncwarp();
+                umma_commit(&empty[s]);
+                umma_commit(&tfull[a]);
             }
+            __syncwarp();
         }
-    } else if (warp == kWarpMask) {
+    } else if (warp == 2) {
         // ===== mask producer: lane owns queries lane + 32*j, j = 0..7 =====
         int cur[8], endp[8], nxt[8];
         int64_t rlo[8];
-        auto rewind = [&]() {     // cursors at the first train item at or after the first global id of this split
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int64_t q = (int64_t)utile * kBM + lane + 32 * j;
-                cur[j] = 0; endp[j] = 0; nxt[j] = 0x7fffffff; rlo[j] = 0;
-                if (p.mask_rowptr && q < p.n_q && n_local > 0) {
-                    const int64_t lo = p.mask_rowptr[q], hi = p.mask_rowptr[q + 1];
-                    const int64_t pos_first = (int64_t)tile_begin * kBN;
-                    const int first_gid = p.item_gids ? __ldg(p.item_gids + pos_first) : (int)(p.item_id_base + pos_first);
-                    int64_t a = lo, b = hi;
-                    while (a < b) {
-                        const int64_t mid = (a + b) >> 1;
-                        if (__ldg(p.mask_col + mid) < first_gid) a = mid + 1; else b = mid;
-                    }
-                    rlo[j] = lo; cur[j] = (int)(a - lo); endp[j] = (int)(hi - lo);
-                    if (cur[j] < endp[j]) nxt[j] = __ldg(p.mask_col + a);
+        for (int j = 0; j < 8; ++j) {
+            const int64_t q = (int64_t)utile * kBM + lane + 32 * j;
+            cur[j] = 0; endp[j] = 0; nxt[j] = 0x7fffffff; rlo[j] = 0;
+            if (p.mask_rowptr && q < p.n_q && n_local > 0) {
+                const int64_t lo = p.mask_rowptr[q], hi = p.mask_rowptr[q + 1];
+                const int64_t pos_first = (int64_t)tile_begin * kBN;
+                const int first_gid = p.item_gids ? __ldg(p.item_gids + pos_first) : (int)(p.item_id_base + pos_first);
+                int64_t a = lo, b = hi;   // first train item at or after the first global id of this split
+                while (a < b) {
+                    const int64_t mid = (a + b) >> 1;
+                    if (__ldg(p.mask_col + mid) < first_gid) a = mid + 1; else b = mid;
                 }
+                rlo[j] = lo; cur[j] = (int)(a - lo); endp[j] = (int)(hi - lo);
+                if (cur[j] < endp[j]) nxt[j] = __ldg(p.mask_col + a);
             }
-        };
-        rewind();
+        }
         uint32_t* sDirty = reinterpret_cast<uint32_t*>(smem + SmemLayout::kDirty);
         for (int w = lane; w < kMaskStages * kChunks * kBM; w += 32) sMask[w] = 0;     // bitmaps start clean and are
         for (int m = 0; m < kMaskStages; ++m) sDirty[m * 32 + lane] = 0;               // cleaned lazily afterwards
         __syncwarp();
         const bool plain = !p.item_gids && !p.item_flags;
-        for (int i = 0; i < n_virtual; ++i) {
-            if (i == T0 && T0 > 0) rewind();        // the sweep proper starts over at tile 0
+        for (int i = 0; i < n_local; ++i) {
             const int a = i % kMaskStages;
             if (i >= kMaskStages) mbar_wait(&mempty[a], ((i / kMaskStages) - 1) & 1);
             uint32_t* mk = sMask + a * kChunks * kBM;
@@ -392,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
                 }
             }
             uint32_t dirty = 0;
-            const int64_t pos0 = (int64_t)(tile_begin + (i < T0 ? i : i - T0)) * kBN;
+            const int64_t pos0 = (int64_t)(tile_begin + i) * kBN;
             int gid_lo = 0, gid_hi = 0;   // global id range covered by this tile: [gid_lo, gid_hi]
             if (plain && pos0 + kBN <= p.n_items) {      // common case: contiguous ids, no flags, full tile
                 gid_lo = (int)(p.item_id_base + pos0);
@@ -442,9 +408,9 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(&mfull[a]);
         }
-    } else if (warp < kEpiWarps) {
+    } else if (warp >= kEpiWarp0) {
         // ===== epilogue: thread = one query = one TMEM lane =====
-        const int e = warp;
+        const int e = warp - kEpiWarp0;
         const int t = e >> 2, quad = warp & 3;
         const int ulocal = t * 128 + quad * 32 + lane;               // query index inside the unit
         const int64_t q = (int64_t)utile * kBM + ulocal;
@@ -473,73 +439,19 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
         Cand* mybuf = p.buf + ((int64_t)split * p.n_q_pad + utile * kBM + ulocal) * CAP;
         float* scratch = sScratch + e * 32;
 
-        bool tile_ready = false;      // tfull of tile i already observed by the probe issued during tile i-1
-        for (int i = 0; i < n_virtual; ++i) {
+        for (int i = 0; i < n_local; ++i) {
             const int a = i % kAcc;
-            if (!tile_ready) mbar_wait(&tfull[a * 2 + t], (i / kAcc) & 1);
+            mbar_wait(&tfull[a], (i / kAcc) & 1);
             const int ms = i % kMaskStages;
+            mbar_wait(&mfull[ms], (i / kMaskStages) & 1);
             tc_fence_after();
-            const int64_t pos0 = (int64_t)(tile_begin + (i < T0 ? i : i - T0)) * kBN;
+            const int64_t pos0 = (int64_t)(tile_begin + i) * kBN;
             const uint32_t acc_addr = tmem_base + lane_addr + kTmemAcc + a * (2 * kBN) + t * kBN;
             uint32_t rbuf[2][32];
-            if (i < T0) {
-                // ---- seed mode: record this query's best unmasked score of the tile, nothing else ----
-                float tmax = -CUDART_INF_F;
-                tile_ready = false;
-#pragma unroll 1
-                for (int c = 0; c < kChunks; ++c) {
-                    tmem_ld32_issue(acc_addr + c * 32, rbuf[0]);
-                    tmem_ld_wait(rbuf[0]);
-                    const uint32_t bad = sMask[(ms * kChunks + c) * kBM + ulocal] | sCommon[ms * kChunks + c];
-                    float m = max32(rbuf[0]);
-                    if (bad) {
-                        m = -CUDART_INF_F;
-#pragma unroll
-                        for (int x = 0; x < 32; ++x)
-                            if (!((bad >> x) & 1u)) m = fmaxf(m, __uint_as_float(rbuf[0][x]));
-                    }
-                    tmax = fmaxf(tmax, m);
-                }
-                reinterpret_cast<float*>(mybuf)[i] = valid ? tmax : -CUDART_INF_F;
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) { mbar_arrive(&tempty[a * 2 + t]); mbar_arrive(&mempty[ms]); }
-                if (i == T0 - 1) {
-                    // the KSEL-th largest of the T0 tile maxima of each query (ties broken by tile index)
-                    for (int L = 0; L < 32; ++L) {
-                        const float* sb = reinterpret_cast<const float*>(mybuf + (int64_t)(L - lane) * CAP);
-                        float ev4[4];
-                        int rk[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int idx = lane + 32 * k;
-                            ev4[k] = idx < T0 ? __ldcg(sb + idx) : -CUDART_INF_F;
-                            rk[k] = 0;
-                        }
-                        for (int j = 0; j < 32; ++j) {
-#pragma unroll
-                            for (int k2 = 0; k2 < 4; ++k2) {
-                                const float sv = __shfl_sync(CR_FULL_MASK, ev4[k2], j);
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) rk[k] += cr::better(sv, j + 32 * k2, ev4[k], lane + 32 * k) ? 1 : 0;
-                            }
-                        }
-                        float t0v = -CUDART_INF_F;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const unsigned who = __ballot_sync(CR_FULL_MASK, rk[k] == KSEL - 1);
-                            if (who) t0v = __shfl_sync(CR_FULL_MASK, ev4[k], __ffs(who) - 1);
-                        }
-                        if (lane == L && valid) thr = t0v;
-                    }
-                    __syncwarp();
-                }
-                continue;
-            }
             if (p.dbg_mode & 1) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(&tempty[a * 2 + t]); mbar_arrive(&mempty[ms]); }
+                if (lane == 0) { mbar_arrive(&tempty[a]); mbar_arrive(&mempty[ms]); }
                 continue;
             }
             tmem_ld32_issue(acc_addr, rbuf[0]);
@@ -548,17 +460,13 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
                 uint32_t (&r)[32] = rbuf[c & 1];
                 tmem_ld_wait(r);
                 if (c + 1 < kChunks) tmem_ld32_issue(acc_addr + (c + 1) * 32, rbuf[(c + 1) & 1]);   // next chunk in flight
-                else tile_ready = (i + 1 < n_virtual) && mbar_test_wait(&tfull[((i + 1) % kAcc) * 2 + t], ((i + 1) / kAcc) & 1);
-                if (p.dbg_scores && blockIdx.x == 0 && i == T0) {
+                if (p.dbg_scores && blockIdx.x == 0 && i == 0) {
 #pragma unroll
                     for (int x = 0; x < 32; ++x) p.dbg_scores[ulocal * kBN + c * 32 + x] = __uint_as_float(r[x]);
                 }
                 const float m = max32(r);
                 unsigned ev = __ballot_sync(CR_FULL_MASK, m > thr);
                 while (ev) {
-                    // slow path (rare): one winning lane per iteration; its 32 values are transposed through shared
-                    // memory so that every lane tests one column.  (A lane-local scan of the 32 registers was tried and
-                    // was 17-35 % slower: 32 predicated compare/append steps cost more issue slots than this.)
                     const int L = __ffs(ev) - 1;
                     ev &= ev - 1;
                     if (lane == L) {
@@ -595,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&tempty[a * 2 + t]); mbar_arrive(&mempty[ms]); }
+            if (lane == 0) { mbar_arrive(&tempty[a]); mbar_arrive(&mempty[ms]); }
         }
         const int64_t o = (int64_t)split * p.n_q_pad + utile * kBM + ulocal;
         p.cnt[o] = valid ? cnt : 0;
@@ -603,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == kWarpAlloc) tmem_dealloc(tmem_base, 512);
+    if (warp == 3) tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------- rescore / verify
@@ -870,8 +778,6 @@ int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_
     sp.tiles_per_split = P.tiles_per_split; sp.n_tiles = P.n_tiles; sp.item_gids = j.item_gids; sp.item_id_base = j.item_id_base;
     sp.mask_rowptr = j.mask_rowptr; sp.mask_col = j.mask_col; sp.item_flags = flags;
     sp.flag_exclude = j.flag_exclude; sp.buf = buf; sp.cnt = cnt; sp.thr = thr; sp.dbg_scores = dbg_scores;
-    sp.seed_tiles = 128;     // = 2*CAP floats: the tile maxima live in the query's (still empty) candidate buffer
-    if (const char* e = getenv("CR_TC_SEED_TILES")) sp.seed_tiles = atoi(e);   // A/B knob for experiments (0 disables)
     {
         const char* e = getenv("CR_TC_DEBUG_MODE");
         sp.dbg_mode = e ? atoi(e) : 0;
