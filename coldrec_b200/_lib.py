@@ -37,6 +37,7 @@ SIGNATURES = {
     "cr_score_topk_f32": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int64, c_int, _P, _P, _P, c_uint8, c_int, _P, _P, _P,
                                   c_int, _P, c_size_t, _P]),
     "cr_debug_tc_tile": (c_int, [_P, c_int64, _P, c_int64, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "cr_debug_tc_timeline": (c_int, [ctypes.POINTER(ctypes.c_ulonglong), c_int]),
     "cr_topk_merge": (c_int, [_P, _P, c_int, c_int64, c_int, _P, _P, _P]),
     "cr_fill_masked": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, c_uint8, _P, _P, _P]),
     "cr_gather_rows_f32": (c_int, [_P, _P, c_int64, c_int, _P, _P]),
@@ -46,6 +47,11 @@ SIGNATURES = {
                                   c_int64, _P, _P]),
     "cr_bn_fold_f32": (c_int, [_P, _P, _P, _P, c_float, c_int, _P, _P, _P]),
     "cr_heater_blend_f32": (c_int, [_P, c_int, _P, _P, c_float, c_float, c_int64, c_int, _P, _P]),
+    "cr_bpr_workspace_bytes": (c_size_t, [c_int64]),
+    "cr_bpr_fwd_bwd_f32": (c_int, [_P, _P, c_int, _P, _P, _P, c_int64, c_float, _P, _P, _P, _P, c_size_t, _P]),
+    "cr_adam_step_f32": (c_int, [_P, _P, _P, _P, c_int64, c_double, c_double, c_double, c_double, c_int64, c_float, _P]),
+    "cr_sample_pairwise": (c_int, [_P, _P, c_int64, _P, _P, c_int32, ctypes.c_uint64, ctypes.c_uint64, c_int64, c_int64, _P, _P, _P,
+                                   _P, _P]),
 }
 
 _lib = None

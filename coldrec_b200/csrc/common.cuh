@@ -52,6 +52,7 @@ int launch_merge(const float* in_score, const int32_t* in_id, int G, int64_t n_q
                  cudaStream_t st, const RefineList* rl, int64_t part_stride, int compact, int64_t gate_lo, int64_t gate_hi);
 size_t tc_workspace_bytes(int64_t n_q, int64_t n_items, int d, int K);
 int launch_tc_scorer(const ExactJob& job, int32_t* n_refined, void* ws, size_t ws_bytes, cudaStream_t st, float* dbg_scores);
+int read_tc_timeline(unsigned long long* host_out, int n_units);
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -42,4 +42,10 @@ int cr_debug_tc_tile(const float* user_tab, int64_t n_q, const float* item_tab, 
     return cr::launch_tc_scorer(job, nullptr, workspace, ws_bytes, (cudaStream_t)stream, dbg);
 }
 
+int cr_debug_tc_timeline(unsigned long long* host_out, int n_units) {
+    int rc = cr::require_device();
+    if (rc != CR_OK) return rc;
+    return cr::read_tc_timeline(host_out, n_units);
+}
+
 }  // extern "C"

@@ -42,7 +42,10 @@ constexpr int kBN = 96;                 // items per tile
 constexpr int kChunks = kBN / 32;       // 32-column epilogue chunks per tile
 constexpr int kStages = 6;              // item smem ring
 constexpr int kAcc = 2;                 // TMEM accumulator stages
-constexpr int kMaskStages = 4;          // mask-bitmap ring (decoupled from the accumulators: ncu r01b showed the
+#ifndef CR_MASK_STAGES
+#define CR_MASK_STAGES 4
+#endif
+constexpr int kMaskStages = CR_MASK_STAGES;          // mask-bitmap ring (decoupled from the accumulators: ncu r01b showed the
                                         // epilogue waiting 40 % of its time on a bitmap tied to the 2 TMEM stages)
 constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;            // first epilogue warp
@@ -171,6 +174,43 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 // ---------------------------------------------------------------------------------------------- sweep
+// Diagnostic timeline (CR_TC_DEBUG_MODE & 8): %globaltimer stamps of epilogue warp 0 of every unit, read back by
+// cr_debug_tc_timeline.  Slots: 0 entry, 1 setup done, 2 queries in TMEM, 3.. after tile 0, 15, 127, 1023, 4095, 8191, last, 10 exit (ns);
+// 11-15 blocked SM cycles: epilogue warp 0 on tfull / on mfull, MMA issuer on full (TMA) / on tempty (epilogue), mask producer on mempty.
+constexpr int kTlSlots = 16, kTlUnits = 8192;
+__device__ unsigned long long g_tc_timeline[kTlUnits * kTlSlots];
+__device__ __forceinline__ unsigned long long globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define CR_TL(slot)                                                                                         \
+    do {                                                                                                    \
+        if constexpr (DBG) {                                                                                \
+            if ((p.dbg_mode & 8) && threadIdx.x == kEpiWarp0 * 32 && blockIdx.x < kTlUnits)                 \
+                g_tc_timeline[blockIdx.x * kTlSlots + (slot)] = globaltimer();                              \
+        }                                                                                                   \
+    } while (0)
+
+// DBG builds account the cycles a role spends blocked on each barrier (slots 11..15 of the unit's timeline row)
+#define CR_WAIT(acc, bar, parity)                                     \
+    do {                                                              \
+        if constexpr (DBG) {                                          \
+            const long long _t0 = clock64();                          \
+            mbar_wait(bar, parity);                                   \
+            acc += clock64() - _t0;                                   \
+        } else {                                                      \
+            mbar_wait(bar, parity);                                   \
+        }                                                             \
+    } while (0)
+#define CR_TL_PUT(slot, value)                                                                              \
+    do {                                                                                                    \
+        if constexpr (DBG) {                                                                                \
+            if ((p.dbg_mode & 8) && lane == 0 && blockIdx.x < kTlUnits)                                     \
+                g_tc_timeline[blockIdx.x * kTlSlots + (slot)] = (unsigned long long)(value);                \
+        }                                                                                                   \
+    } while (0)
+
 struct SweepParams {
     const float* Q;          // [n_q, 64] gathered query vectors
     int64_t n_q;             // valid queries
@@ -189,6 +229,7 @@ struct SweepParams {
     int* cnt;                // [S][n_q_pad]
     float* thr;              // [S][n_q_pad]
     float* dbg_scores;       // optional: raw TF32 scores of the first 256 x 96 block (probe)
+    int seed_tiles;          // threshold seed phase: the first seed_tiles tiles are swept twice (see the kernel)
     int dbg_mode;            // timing experiments only (env CR_TC_DEBUG_MODE): 1 = skip TMEM loads, 2 = skip MMAs, 4 = interleave
 };
 
@@ -196,10 +237,10 @@ struct SmemLayout {
     static constexpr int kB = 0;                                       // kStages x 24 KB
     static constexpr int kMask = kB + kStages * kTileBytes;            // [kMaskStages][kChunks][256 queries] u32
     static constexpr int kCommon = kMask + kMaskStages * kChunks * kBM * 4;   // [kMaskStages][kChunks] u32 (padded to 64 B)
-    static constexpr int kDirty = kCommon + 64;                        // [kMaskStages][32 lanes] u32: words a lane must clear
+    static constexpr int kDirty = kCommon + ((kMaskStages * kChunks * 4 + 63) / 64) * 64;                        // [kMaskStages][32 lanes] u32: words a lane must clear
     static constexpr int kScratch = kDirty + kMaskStages * 32 * 4;     // 8 warps x 32 floats
     static constexpr int kBars = kScratch + 8 * 128;
-    static constexpr int kTotal = kBars + 256;
+    static constexpr int kTotal = kBars + 512;
 };
 
 // Rank-compact one query's candidate buffer to its best KSEL entries, sorted; returns the KSEL-th score.
@@ -238,7 +279,47 @@ __device__ float warp_shrink(Cand* buf, int cnt, int ksel, int lane) {
     return thr;
 }
 
+// End of the seed phase: every lane's query gets the KSEL-th largest of its T0 tile maxima (ties broken by tile index), one
+// ulp lower so that the item that set the bound still passes "score > thr" (at least KSEL items do).  Each lane passes the
+// base of ITS query's buffer; lane L's buffer is ranked by the whole warp.  Once per unit: kept out of line.
 template <int KSEL>
+__device__ __noinline__ float seed_threshold(const float* mine, int cap, int T0, int lane, bool valid) {
+    float thr = CUDART_INF_F;                    // padding lanes never take the slow path
+    __syncwarp();
+    for (int L = 0; L < 32; ++L) {
+        const float* sb = mine + (int64_t)(L - lane) * cap * 2;      // cap Cand entries = 2*cap floats per query
+        float ev4[4];
+        int rk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = lane + 32 * k;
+            ev4[k] = idx < T0 ? __ldcg(sb + idx) : -CUDART_INF_F;
+            rk[k] = 0;
+        }
+        for (int j = 0; j < 32; ++j) {
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+                const float sv = __shfl_sync(CR_FULL_MASK, ev4[k2], j);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) rk[k] += cr::better(sv, j + 32 * k2, ev4[k], lane + 32 * k) ? 1 : 0;
+            }
+        }
+        float t0v = -CUDART_INF_F;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned who = __ballot_sync(CR_FULL_MASK, rk[k] == KSEL - 1);
+            if (who) t0v = __shfl_sync(CR_FULL_MASK, ev4[k], __ffs(who) - 1);
+        }
+        if (lane == L && valid) thr = t0v > -CUDART_INF_F ? nextafterf(t0v, -CUDART_INF_F) : -CUDART_INF_F;
+    }
+    __syncwarp();
+    return thr;
+}
+
+// DBG = true compiles the probe / timing hooks (dbg_scores, dbg_mode, timeline) in; the production instantiation has none
+// of them: the hot loops of the four warp roles must stay inside the 32 KB L1.5 instruction cache (B300_MICROARCH.md) —
+// an earlier seed-phase variant that grew the kernel from 43 KB to 57 KB of SASS ran 14 % slower with identical hot loops.
+template <int KSEL, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_i, const SweepParams p) {
     constexpr int CAP = KSEL + 32;
     constexpr int EPL = CAP / 32;
@@ -263,6 +344,16 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
     const int tile_begin = split * p.tiles_per_split;
     const int tile_end = min(p.n_tiles, tile_begin + p.tiles_per_split);
     const int n_local = tile_end - tile_begin;
+    // Threshold seed phase.  A query's threshold starts at -inf, so the first ~10^5 items of every sweep flood the slow
+    // path: the per-unit timeline (CR_TC_DEBUG_MODE=8, profiles/r01_sweep_timeline.txt) shows 31 us per tile over the
+    // first 16 tiles, 7 us up to tile 127, 1.7 us up to tile 1023 against 0.66 us in steady state — 2.1 ms lost per
+    // unit, whatever the length of the sweep.  So the first T0 tiles are first swept in "seed mode": the epilogue only
+    // records each query's best unmasked score per tile; T0 distinct items reach the KSEL-th largest of those T0 tile
+    // maxima, so it is a valid lower bound of the query's KSEL-th best score, and the real sweep — which starts over at
+    // tile 0 — begins with a threshold that is already tight.  Virtual tile v = tile v (seed, v < T0) or v - T0 (sweep).
+    const int T0 = (p.seed_tiles > 0 && n_local >= 8 * p.seed_tiles) ? p.seed_tiles : 0;
+    const int n_virtual = n_local + T0;
+    CR_TL(0);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -277,15 +368,16 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    CR_TL(1);
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int i = 0; i < n_local; ++i) {
+            for (int i = 0; i < n_virtual; ++i) {
                 const int s = i % kStages;
                 if (i >= kStages) mbar_wait(&empty[s], ((i / kStages) - 1) & 1);
                 mbar_expect_tx(&full[s], kTileBytes);
-                const int row = (tile_begin + i) * kBN;
+                const int row = (tile_begin + (i < T0 ? i : i - T0)) * kBN;
                 tma_load_2d(sB + s * kTileBytes, &map_i, &full[s], 0, row);
                 tma_load_2d(sB + s * kTileBytes + kChunkBytes, &map_i, &full[s], 32, row);
             }
@@ -295,17 +387,18 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
         mbar_wait(aready, 0);
         tc_fence_after();
         const bool leader = elect_one();
+        [[maybe_unused]] long long w_tempty = 0, w_full = 0;
         // B descriptor = constant high word | (start address >> 4): per MMA only the low word moves
         constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
-        for (int i = 0; i < n_local; ++i) {
+        for (int i = 0; i < n_virtual; ++i) {
             const int s = i % kStages, a = i % kAcc;
-            if (i >= kAcc) mbar_wait(&tempty[a], ((i / kAcc) - 1) & 1);
-            mbar_wait(&full[s], (i / kStages) & 1);
+            if (i >= kAcc) CR_WAIT(w_tempty, &tempty[a], ((i / kAcc) - 1) & 1);
+            CR_WAIT(w_full, &full[s], (i / kStages) & 1);
             tc_fence_after();
             if (leader) {
                 const uint32_t dlo = ((smem_u32(sB + s * kTileBytes) >> 4) & 0x3FFF) | (1u << 16);
                 const uint32_t d0 = tmem_base + kTmemAcc + a * (2 * kBN);
-                if (!(p.dbg_mode & 2)) {
+                if (!DBG || !(p.dbg_mode & 2)) {
 #pragma unroll
                     for (int m = 0; m < 16; ++m) {
                         const int t = m >> 3, k = m & 7;
@@ -319,95 +412,131 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
             }
             __syncwarp();
         }
+        CR_TL_PUT(13, w_full);
+        CR_TL_PUT(14, w_tempty);
     } else if (warp == 2) {
         // ===== mask producer: lane owns queries lane + 32*j, j = 0..7 =====
-        int cur[8], endp[8], nxt[8];
+        // nxt[j] = next train item of the query, nx2[j] = the one after it, loaded one consumption EARLY: advancing a
+        // cursor must not wait for a global load.  (With the load issued at the advance, every tile holding a train item
+        // stalled this warp for a DRAM round trip per query; at 100 train items x 256 queries per unit that was a fixed
+        // ~3 ms per unit however long the sweep — 4 % of a 10M-item sweep, 25 % of a 1.25M-item shard.)
+        int cur[8], endp[8], nxt[8], nx2[8];
         int64_t rlo[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int64_t q = (int64_t)utile * kBM + lane + 32 * j;
-            cur[j] = 0; endp[j] = 0; nxt[j] = 0x7fffffff; rlo[j] = 0;
-            if (p.mask_rowptr && q < p.n_q && n_local > 0) {
-                const int64_t lo = p.mask_rowptr[q], hi = p.mask_rowptr[q + 1];
-                const int64_t pos_first = (int64_t)tile_begin * kBN;
-                const int first_gid = p.item_gids ? __ldg(p.item_gids + pos_first) : (int)(p.item_id_base + pos_first);
-                int64_t a = lo, b = hi;   // first train item at or after the first global id of this split
-                while (a < b) {
-                    const int64_t mid = (a + b) >> 1;
-                    if (__ldg(p.mask_col + mid) < first_gid) a = mid + 1; else b = mid;
-                }
-                rlo[j] = lo; cur[j] = (int)(a - lo); endp[j] = (int)(hi - lo);
-                if (cur[j] < endp[j]) nxt[j] = __ldg(p.mask_col + a);
-            }
-        }
         uint32_t* sDirty = reinterpret_cast<uint32_t*>(smem + SmemLayout::kDirty);
         for (int w = lane; w < kMaskStages * kChunks * kBM; w += 32) sMask[w] = 0;     // bitmaps start clean and are
         for (int m = 0; m < kMaskStages; ++m) sDirty[m * 32 + lane] = 0;               // cleaned lazily afterwards
         __syncwarp();
         const bool plain = !p.item_gids && !p.item_flags;
-        for (int i = 0; i < n_local; ++i) {
-            const int a = i % kMaskStages;
-            if (i >= kMaskStages) mbar_wait(&mempty[a], ((i / kMaskStages) - 1) & 1);
-            uint32_t* mk = sMask + a * kChunks * kBM;
-            {   // clear only the words this lane set the last time the stage was used (bit b -> chunk b%3, query lane+32*(b/3))
-                uint32_t dm = sDirty[a * 32 + lane];
-                while (dm) {
-                    const int b = __ffs(dm) - 1;
-                    dm &= dm - 1;
-                    mk[(b % kChunks) * kBM + lane + 32 * (b / kChunks)] = 0;
-                }
-            }
-            uint32_t dirty = 0;
-            const int64_t pos0 = (int64_t)(tile_begin + i) * kBN;
-            int gid_lo = 0, gid_hi = 0;   // global id range covered by this tile: [gid_lo, gid_hi]
-            if (plain && pos0 + kBN <= p.n_items) {      // common case: contiguous ids, no flags, full tile
-                gid_lo = (int)(p.item_id_base + pos0);
-                gid_hi = gid_lo + kBN - 1;
-                if (lane < kChunks) sCommon[a * kChunks + lane] = 0;
-            } else {
-#pragma unroll
-                for (int c = 0; c < kChunks; ++c) {
-                    const int64_t pos = pos0 + c * 32 + lane;
-                    bool bad = pos >= p.n_items;
-                    int gid = 0x7fffffff;
-                    if (!bad) {
-                        gid = p.item_gids ? __ldg(p.item_gids + pos) : (int)(p.item_id_base + pos);
-                        if (p.item_flags) bad = (__ldg(p.item_flags + gid) & p.flag_exclude) != 0;
-                    }
-                    const unsigned bits = __ballot_sync(CR_FULL_MASK, bad);
-                    if (lane == 0) sCommon[a * kChunks + c] = bits;
-                    if (c == 0) gid_lo = __shfl_sync(CR_FULL_MASK, gid, 0);
-                    const unsigned valid = __ballot_sync(CR_FULL_MASK, pos < p.n_items);
-                    if (valid) gid_hi = __shfl_sync(CR_FULL_MASK, gid, 31 - __clz(valid));
-                }
-            }
-            __syncwarp();
+        // Cursor setup: first train item at or after the first global id of this split.  The eight binary searches of a lane
+        // advance together (eight independent loads per step instead of 8 x 7 dependent DRAM round trips, ~50 us per unit).
+        int cur0[8];
+        {
+            int64_t lo8[8], hi8[8];
+            const int64_t pos_first = (int64_t)tile_begin * kBN;
+            const int first_gid = (p.item_gids && n_local > 0) ? __ldg(p.item_gids + pos_first) : (int)(p.item_id_base + pos_first);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                while (nxt[j] <= gid_hi) {
-                    int pos = -1;
-                    if (!p.item_gids) {
-                        pos = nxt[j] - gid_lo;
-                    } else if (nxt[j] >= gid_lo) {   // locate the id inside this tile of the compacted table
-                        int lo2 = 0, hi2 = (int)min((int64_t)kBN, p.n_items - pos0);
-                        while (lo2 < hi2) {
-                            const int mid = (lo2 + hi2) >> 1;
-                            if (__ldg(p.item_gids + pos0 + mid) < nxt[j]) lo2 = mid + 1; else hi2 = mid;
-                        }
-                        if (pos0 + lo2 < p.n_items && __ldg(p.item_gids + pos0 + lo2) == nxt[j]) pos = lo2;
-                    }
-                    if (pos >= 0 && pos < kBN) {
-                        mk[(pos >> 5) * kBM + lane + 32 * j] |= 1u << (pos & 31);
-                        dirty |= 1u << (j * kChunks + (pos >> 5));
-                    }
-                    ++cur[j];
-                    nxt[j] = (cur[j] < endp[j]) ? __ldg(p.mask_col + rlo[j] + cur[j]) : 0x7fffffff;
+                const int64_t q = (int64_t)utile * kBM + lane + 32 * j;
+                lo8[j] = hi8[j] = 0; rlo[j] = 0; endp[j] = 0;
+                if (p.mask_rowptr && q < p.n_q && n_local > 0) {
+                    lo8[j] = p.mask_rowptr[q]; hi8[j] = p.mask_rowptr[q + 1];
+                    rlo[j] = lo8[j]; endp[j] = (int)(hi8[j] - lo8[j]);
                 }
             }
-            sDirty[a * 32 + lane] = dirty;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&mfull[a]);
+            bool more = true;
+            while (more) {
+                more = false;
+                int v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = lo8[j] < hi8[j] ? __ldg(p.mask_col + ((lo8[j] + hi8[j]) >> 1)) : 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (lo8[j] < hi8[j]) {
+                        const int64_t mid = (lo8[j] + hi8[j]) >> 1;
+                        if (v[j] < first_gid) lo8[j] = mid + 1; else hi8[j] = mid;
+                        more |= lo8[j] < hi8[j];
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cur0[j] = (int)(lo8[j] - rlo[j]);
         }
+        [[maybe_unused]] long long w_mempty = 0;
+        // two passes over the tiles when the seed phase is on: [0, T0) in seed mode, then the whole sweep from tile 0
+        for (int pass = (T0 > 0 ? 0 : 1), i = 0; pass < 2; ++pass) {
+            const int n_pass = pass == 0 ? T0 : n_local;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                cur[j] = cur0[j];
+                nxt[j] = (cur[j] < endp[j]) ? __ldg(p.mask_col + rlo[j] + cur[j]) : 0x7fffffff;
+                nx2[j] = (cur[j] + 1 < endp[j]) ? __ldg(p.mask_col + rlo[j] + cur[j] + 1) : 0x7fffffff;
+            }
+            for (int k = 0; k < n_pass; ++k, ++i) {
+                const int a = i % kMaskStages;
+                if (i >= kMaskStages) CR_WAIT(w_mempty, &mempty[a], ((i / kMaskStages) - 1) & 1);
+                uint32_t* mk = sMask + a * kChunks * kBM;
+                {   // clear only the words this lane set the last time the stage was used (bit b -> chunk b%3, query lane+32*(b/3))
+                    uint32_t dm = sDirty[a * 32 + lane];
+                    while (dm) {
+                        const int b = __ffs(dm) - 1;
+                        dm &= dm - 1;
+                        mk[(b % kChunks) * kBM + lane + 32 * (b / kChunks)] = 0;
+                    }
+                }
+                uint32_t dirty = 0;
+                const int64_t pos0 = (int64_t)(tile_begin + k) * kBN;
+                int gid_lo = 0, gid_hi = 0;   // global id range covered by this tile: [gid_lo, gid_hi]
+                if (plain && pos0 + kBN <= p.n_items) {      // common case: contiguous ids, no flags, full tile
+                    gid_lo = (int)(p.item_id_base + pos0);
+                    gid_hi = gid_lo + kBN - 1;
+                    if (lane < kChunks) sCommon[a * kChunks + lane] = 0;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < kChunks; ++c) {
+                        const int64_t pos = pos0 + c * 32 + lane;
+                        bool bad = pos >= p.n_items;
+                        int gid = 0x7fffffff;
+                        if (!bad) {
+                            gid = p.item_gids ? __ldg(p.item_gids + pos) : (int)(p.item_id_base + pos);
+                            if (p.item_flags) bad = (__ldg(p.item_flags + gid) & p.flag_exclude) != 0;
+                        }
+                        const unsigned bits = __ballot_sync(CR_FULL_MASK, bad);
+                        if (lane == 0) sCommon[a * kChunks + c] = bits;
+                        if (c == 0) gid_lo = __shfl_sync(CR_FULL_MASK, gid, 0);
+                        const unsigned valid = __ballot_sync(CR_FULL_MASK, pos < p.n_items);
+                        if (valid) gid_hi = __shfl_sync(CR_FULL_MASK, gid, 31 - __clz(valid));
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    while (nxt[j] <= gid_hi) {
+                        int pos = -1;
+                        if (!p.item_gids) {
+                            pos = nxt[j] - gid_lo;
+                        } else if (nxt[j] >= gid_lo) {   // locate the id inside this tile of the compacted table
+                            int lo2 = 0, hi2 = (int)min((int64_t)kBN, p.n_items - pos0);
+                            while (lo2 < hi2) {
+                                const int mid = (lo2 + hi2) >> 1;
+                                if (__ldg(p.item_gids + pos0 + mid) < nxt[j]) lo2 = mid + 1; else hi2 = mid;
+                            }
+                            if (pos0 + lo2 < p.n_items && __ldg(p.item_gids + pos0 + lo2) == nxt[j]) pos = lo2;
+                        }
+                        if (pos >= 0 && pos < kBN) {
+                            mk[(pos >> 5) * kBM + lane + 32 * j] |= 1u << (pos & 31);
+                            dirty |= 1u << (j * kChunks + (pos >> 5));
+                        }
+                        ++cur[j];
+                        nxt[j] = nx2[j];
+                        nx2[j] = (cur[j] + 1 < endp[j]) ? __ldg(p.mask_col + rlo[j] + cur[j] + 1) : 0x7fffffff;
+                    }
+                }
+                sDirty[a * 32 + lane] = dirty;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&mfull[a]);
+            }
+        }
+        CR_TL_PUT(15, w_mempty);
     } else if (warp >= kEpiWarp0) {
         // ===== epilogue: thread = one query = one TMEM lane =====
         const int e = warp - kEpiWarp0;
@@ -434,25 +563,32 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(aready);
         }
-        float thr = valid ? -CUDART_INF_F : CUDART_INF_F;
+        CR_TL(2);
+        // seed phase: thr = +inf keeps every lane off the slow path while the tile maxima are collected
+        float thr = (valid && T0 == 0) ? -CUDART_INF_F : CUDART_INF_F;
+        float tmax = -CUDART_INF_F;
+        [[maybe_unused]] long long w_tfull = 0, w_mfull = 0;
         int cnt = 0;
         Cand* mybuf = p.buf + ((int64_t)split * p.n_q_pad + utile * kBM + ulocal) * CAP;
         float* scratch = sScratch + e * 32;
 
-        for (int i = 0; i < n_local; ++i) {
+        for (int i = 0; i < n_virtual; ++i) {
             const int a = i % kAcc;
-            mbar_wait(&tfull[a], (i / kAcc) & 1);
+            CR_WAIT(w_tfull, &tfull[a], (i / kAcc) & 1);
             const int ms = i % kMaskStages;
-            mbar_wait(&mfull[ms], (i / kMaskStages) & 1);
+            CR_WAIT(w_mfull, &mfull[ms], (i / kMaskStages) & 1);
             tc_fence_after();
-            const int64_t pos0 = (int64_t)(tile_begin + i) * kBN;
+            const bool seeding = i < T0;
+            const int64_t pos0 = (int64_t)(tile_begin + (seeding ? i : i - T0)) * kBN;
             const uint32_t acc_addr = tmem_base + lane_addr + kTmemAcc + a * (2 * kBN) + t * kBN;
             uint32_t rbuf[2][32];
-            if (p.dbg_mode & 1) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) { mbar_arrive(&tempty[a]); mbar_arrive(&mempty[ms]); }
-                continue;
+            if constexpr (DBG) {
+                if (p.dbg_mode & 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(&tempty[a]); mbar_arrive(&mempty[ms]); }
+                    continue;
+                }
             }
             tmem_ld32_issue(acc_addr, rbuf[0]);
 #pragma unroll
@@ -460,13 +596,23 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
                 uint32_t (&r)[32] = rbuf[c & 1];
                 tmem_ld_wait(r);
                 if (c + 1 < kChunks) tmem_ld32_issue(acc_addr + (c + 1) * 32, rbuf[(c + 1) & 1]);   // next chunk in flight
-                if (p.dbg_scores && blockIdx.x == 0 && i == 0) {
+                if constexpr (DBG) {
+                    if (p.dbg_scores && blockIdx.x == 0 && i == T0) {
 #pragma unroll
-                    for (int x = 0; x < 32; ++x) p.dbg_scores[ulocal * kBN + c * 32 + x] = __uint_as_float(r[x]);
+                        for (int x = 0; x < 32; ++x) p.dbg_scores[ulocal * kBN + c * 32 + x] = __uint_as_float(r[x]);
+                    }
                 }
-                const float m = max32(r);
+                float m = max32(r);
+                if (seeding) {      // (warp-uniform) seed mode: this query's best score over the chunks free of masked items
+                    const uint32_t bad = sMask[(ms * kChunks + c) * kBM + ulocal] | sCommon[ms * kChunks + c];
+                    if (bad) m = -CUDART_INF_F;      // a chunk holding a masked item is skipped: the bound stays valid, barely weaker
+                    tmax = fmaxf(tmax, m);
+                }
                 unsigned ev = __ballot_sync(CR_FULL_MASK, m > thr);
                 while (ev) {
+                    // slow path (rare): one winning lane per iteration; its 32 values are transposed through shared
+                    // memory so that every lane tests one column.  (A lane-local scan of the 32 registers was tried and
+                    // was 17-35 % slower: 32 predicated compare/append steps cost more issue slots than this.)
                     const int L = __ffs(ev) - 1;
                     ev &= ev - 1;
                     if (lane == L) {
@@ -504,13 +650,28 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(&tempty[a]); mbar_arrive(&mempty[ms]); }
+            if (seeding) {
+                // the tile maxima live in the query's (still empty) candidate buffer: 2*CAP floats >= T0
+                reinterpret_cast<float*>(mybuf)[i] = valid ? tmax : -CUDART_INF_F;
+                tmax = -CUDART_INF_F;
+                if (i == T0 - 1) thr = seed_threshold<KSEL>(reinterpret_cast<const float*>(mybuf), CAP, T0, lane, valid);
+            }
+            if constexpr (DBG) {
+                if (p.dbg_mode & 8) {
+                    const int v = i - T0;
+                    const int slot = v == 0 ? 3 : v == 15 ? 4 : v == 127 ? 5 : v == 1023 ? 6 : v == 4095 ? 7 : v == 8191 ? 8 : v == n_local - 1 ? 9 : -1;
+                    if (slot >= 0) CR_TL(slot);
+                }
+            }
         }
+        if (e == 0) { CR_TL_PUT(11, w_tfull); CR_TL_PUT(12, w_mfull); }
         const int64_t o = (int64_t)split * p.n_q_pad + utile * kBM + ulocal;
         p.cnt[o] = valid ? cnt : 0;
         p.thr[o] = thr;
     }
     tc_fence_before();
     __syncthreads();
+    CR_TL(10);
     if (warp == 3) tmem_dealloc(tmem_base, 512);
 }
 
@@ -778,19 +939,23 @@ int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_
     sp.tiles_per_split = P.tiles_per_split; sp.n_tiles = P.n_tiles; sp.item_gids = j.item_gids; sp.item_id_base = j.item_id_base;
     sp.mask_rowptr = j.mask_rowptr; sp.mask_col = j.mask_col; sp.item_flags = flags;
     sp.flag_exclude = j.flag_exclude; sp.buf = buf; sp.cnt = cnt; sp.thr = thr; sp.dbg_scores = dbg_scores;
+    sp.seed_tiles = 128;     // <= 2*CAP: the tile maxima live in the query's (still empty) candidate buffer
+    if (const char* e = getenv("CR_TC_SEED_TILES")) sp.seed_tiles = min(128, max(0, atoi(e)));   // A/B knob (0 disables)
     {
         const char* e = getenv("CR_TC_DEBUG_MODE");
         sp.dbg_mode = e ? atoi(e) : 0;
     }
     const unsigned grid = (unsigned)(P.n_utiles * P.S);
     prof_start(PROF_SCORE_SWEEP, st);
-    if (P.ksel == 32) {
-        CR_CUDA_TRY(cudaFuncSetAttribute(score_sweep_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::kTotal));
-        score_sweep_tc_kernel<32><<<grid, kThreads, SmemLayout::kTotal, st>>>(map_i, sp);
-    } else {
-        CR_CUDA_TRY(cudaFuncSetAttribute(score_sweep_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::kTotal));
-        score_sweep_tc_kernel<64><<<grid, kThreads, SmemLayout::kTotal, st>>>(map_i, sp);
-    }
+    const bool dbg = sp.dbg_mode != 0 || dbg_scores != nullptr;
+#define CR_SWEEP(KS, DB)                                                                                                        \
+    do {                                                                                                                        \
+        CR_CUDA_TRY(cudaFuncSetAttribute(score_sweep_tc_kernel<KS, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::kTotal)); \
+        score_sweep_tc_kernel<KS, DB><<<grid, kThreads, SmemLayout::kTotal, st>>>(map_i, sp);                                   \
+    } while (0)
+    if (P.ksel == 32) { if (dbg) CR_SWEEP(32, true); else CR_SWEEP(32, false); }
+    else { if (dbg) CR_SWEEP(64, true); else CR_SWEEP(64, false); }
+#undef CR_SWEEP
     CR_LAUNCH_CHECK("score_sweep_tc_kernel");
     prof_stop(PROF_SCORE_SWEEP, st);
 
@@ -819,6 +984,12 @@ int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_
     rc = launch_exact_refine(ej, RefineList{rlist, rcount, n_q}, base + P.off_exact, P.exact_bytes, st);
     if (rc != CR_OK) return rc;
     if (n_refined) CR_CUDA_TRY(cudaMemcpyAsync(n_refined, rcount, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return CR_OK;
+}
+
+int read_tc_timeline(unsigned long long* host_out, int n_units) {
+    if (!host_out || n_units < 0 || n_units > kTlUnits) return CR_ERR_ARG;
+    CR_CUDA_TRY(cudaMemcpyFromSymbol(host_out, g_tc_timeline, (size_t)n_units * kTlSlots * sizeof(unsigned long long)));
     return CR_OK;
 }
 

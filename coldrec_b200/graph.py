@@ -96,26 +96,30 @@ def bipartite_norm_csr(user_idx: torch.Tensor, item_idx: torch.Tensor, user_num:
     return CsrGraph(rowptr, cols.to(torch.int32), val, n)
 
 
-def propagate(graph: CsrGraph, user_emb: torch.Tensor, item_emb: torch.Tensor, n_layers: int, include_ego: bool = True,
-              return_layers: bool = False):
-    """E0 = [U; I];  E_{k+1} = A.E_k;  result = mean over layers 0..L (LightGCN, model/LightGCN.py:86-96)
-    or 1..L (``include_ego=False``: SimGCL/XSimGCL eval path, model/SimGCL.py:101-113).
+class PropagationBuffers:
+    """Scratch of one propagation over an (N, d) table: the layer-mean accumulator and two ping-pong layer tables.
+    Reusing one instance across calls (training steps, epochs) keeps the hot loop free of allocations."""
 
-    One SpMM launch group per layer; the running layer sum and the final division live in the SpMM
-    epilogue, so no (N, L+1, d) stack is ever materialised.  ``return_layers`` additionally returns
-    [E_0 (if include_ego), E_1, ..., E_L] like NCL's encoder (model/NCL.py:186-196).
-    """
+    def __init__(self, n: int, d: int, device):
+        self.acc = torch.empty((n, d), dtype=torch.float32, device=device)
+        self.ping = [torch.empty((n, d), dtype=torch.float32, device=device) for _ in range(2)]
+
+
+def propagate_table(graph: CsrGraph, ego: torch.Tensor, n_layers: int, include_ego: bool = True, return_layers: bool = False,
+                    buffers: Optional[PropagationBuffers] = None):
+    """``propagate`` on the concatenated (N, d) table ``ego = [U; I]``; returns the (N, d) layer mean (a view of
+    ``buffers.acc`` when buffers are given) and, with ``return_layers``, the list of layer tables."""
     if n_layers < 1:
         raise ValueError("n_layers must be >= 1")
-    n_u = user_emb.shape[0]
-    ego = torch.cat([user_emb, item_emb], 0).contiguous()
     if ego.shape[0] != graph.n_cols or graph.n_rows != graph.n_cols:
         raise ValueError(f"adjacency is {graph.n_rows}x{graph.n_cols}, embeddings have {ego.shape[0]} rows")
     count = n_layers + (1 if include_ego else 0)
-    acc = torch.empty_like(ego)
+    acc = buffers.acc if buffers is not None else torch.empty_like(ego)
     layers: List[torch.Tensor] = [ego] if include_ego else []
     x = ego
-    bufs = [torch.empty_like(ego), torch.empty_like(ego)] if (n_layers > 1 and not return_layers) else None
+    bufs = None
+    if n_layers > 1 and not return_layers:
+        bufs = buffers.ping if buffers is not None else [torch.empty_like(ego), torch.empty_like(ego)]
     for k in range(1, n_layers + 1):
         last = k == n_layers
         need_y = (not last) or return_layers
@@ -128,8 +132,24 @@ def propagate(graph: CsrGraph, user_emb: torch.Tensor, item_emb: torch.Tensor, n
         if return_layers:
             layers.append(y)
         x = y
+    return (acc, layers) if return_layers else acc
+
+
+def propagate(graph: CsrGraph, user_emb: torch.Tensor, item_emb: torch.Tensor, n_layers: int, include_ego: bool = True,
+              return_layers: bool = False):
+    """E0 = [U; I];  E_{k+1} = A.E_k;  result = mean over layers 0..L (LightGCN, model/LightGCN.py:86-96)
+    or 1..L (``include_ego=False``: SimGCL/XSimGCL eval path, model/SimGCL.py:101-113).
+
+    One SpMM launch group per layer; the running layer sum and the final division live in the SpMM
+    epilogue, so no (N, L+1, d) stack is ever materialised.  ``return_layers`` additionally returns
+    [E_0 (if include_ego), E_1, ..., E_L] like NCL's encoder (model/NCL.py:186-196).
+    """
+    n_u = user_emb.shape[0]
+    ego = torch.cat([user_emb, item_emb], 0).contiguous()
     if return_layers:
+        acc, layers = propagate_table(graph, ego, n_layers, include_ego, True)
         return acc[:n_u], acc[n_u:], layers
+    acc = propagate_table(graph, ego, n_layers, include_ego)
     return acc[:n_u], acc[n_u:]
 
 

@@ -14,7 +14,7 @@ import torch
 from . import _lib
 
 __all__ = ["spmm_plan", "spmm", "spmm_bcast", "score_topk", "topk_merge", "fill_masked", "gather_rows", "rank_metrics", "linear_act", "bn_fold",
-           "heater_blend", "SCORE_EXACT_F32", "SCORE_TF32_CHECKED"]
+           "heater_blend", "bpr_fwd_bwd", "adam_step", "sample_pairwise", "SCORE_EXACT_F32", "SCORE_TF32_CHECKED"]
 
 SCORE_EXACT_F32 = _lib.SCORE_EXACT_F32
 SCORE_TF32_CHECKED = _lib.SCORE_TF32_CHECKED
@@ -323,3 +323,72 @@ def heater_blend(gate, expert, Vin, keep: float, one_minus_keep: float):
                                      _ptr(out), _stream(dev))
     _lib.check(rc, "cr_heater_blend_f32")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ K5 / K6
+def bpr_fwd_bwd(user_emb, item_emb, u_idx, i_idx, j_idx, reg: float, grad_user, grad_item, loss=None, workspace=None):
+    """BPR + L2 loss of one batch and its gradients w.r.t. the gathered rows, accumulated into the dense
+    gradient tables (which the caller zeroed).  Returns loss fp32[4] on device: total, bpr, reg, 0."""
+    lib = _lib.load()
+    user_emb = _req(user_emb, torch.float32, "user_emb"); item_emb = _req(item_emb, torch.float32, "item_emb")
+    u_idx = _req(u_idx, torch.int32, "u_idx"); i_idx = _req(i_idx, torch.int32, "i_idx"); j_idx = _req(j_idx, torch.int32, "j_idx")
+    grad_user = _req(grad_user, torch.float32, "grad_user"); grad_item = _req(grad_item, torch.float32, "grad_item")
+    dev = _same_device(user_emb, item_emb, u_idx, i_idx, j_idx, grad_user, grad_item)
+    if user_emb.dim() != 2 or item_emb.dim() != 2 or user_emb.shape[1] != item_emb.shape[1]:
+        raise ValueError("user_emb and item_emb must be 2-D with the same width")
+    if grad_user.shape != user_emb.shape or grad_item.shape != item_emb.shape:
+        raise ValueError("gradient tables must have the shapes of the embedding tables")
+    B = u_idx.numel()
+    if i_idx.numel() != B or j_idx.numel() != B:
+        raise ValueError("u_idx / i_idx / j_idx differ in length")
+    if loss is None:
+        loss = torch.zeros(4, dtype=torch.float32, device=dev)
+    _req(loss, torch.float32, "loss")
+    need = lib.cr_bpr_workspace_bytes(B)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cr_bpr_fwd_bwd_f32(_ptr(user_emb), _ptr(item_emb), user_emb.shape[1], _ptr(u_idx), _ptr(i_idx), _ptr(j_idx), B,
+                                    float(reg), _ptr(loss), _ptr(grad_user), _ptr(grad_item), _ptr(workspace), workspace.numel(),
+                                    _stream(dev))
+    _lib.check(rc, "cr_bpr_fwd_bwd_f32")
+    return loss
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step: int, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0):
+    """In-place torch.optim.Adam update of one fp32 tensor (state tensors updated in place as well)."""
+    lib = _lib.load()
+    for t, name in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _req(t, torch.float32, name)
+        if t.numel() != param.numel():
+            raise ValueError(f"{name} has {t.numel()} elements, param has {param.numel()}")
+    dev = _same_device(param, grad, exp_avg, exp_avg_sq)
+    with torch.cuda.device(dev):
+        rc = lib.cr_adam_step_f32(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(lr), float(betas[0]),
+                                  float(betas[1]), float(eps), int(step), float(grad_scale), _stream(dev))
+    _lib.check(rc, "cr_adam_step_f32")
+    return param
+
+
+def sample_pairwise(pair_user, pair_item, train_rowptr, train_col, n_items: int, seed: int, epoch: int, begin: int, count: int,
+                    out=None, n_exhausted=None):
+    """(user, positive, negative) triples of positions [begin, begin+count) of epoch `epoch`'s shuffled pair list."""
+    lib = _lib.load()
+    pair_user = _req(pair_user, torch.int32, "pair_user"); pair_item = _req(pair_item, torch.int32, "pair_item")
+    train_rowptr = _req(train_rowptr, torch.int64, "train_rowptr"); train_col = _req(train_col, torch.int32, "train_col")
+    n_exhausted = _req(n_exhausted, torch.int32, "n_exhausted", optional=True)
+    dev = _same_device(pair_user, pair_item, train_rowptr, train_col, n_exhausted)
+    n_pairs = pair_user.numel()
+    if pair_item.numel() != n_pairs:
+        raise ValueError("pair_user / pair_item differ in length")
+    if out is None:
+        out = torch.empty((3, count), dtype=torch.int32, device=dev)
+    _req(out, torch.int32, "out")
+    if out.shape[0] != 3 or out.shape[1] < count:
+        raise ValueError("out must be int32 [3, >=count]")
+    with torch.cuda.device(dev):
+        rc = lib.cr_sample_pairwise(_ptr(pair_user), _ptr(pair_item), n_pairs, _ptr(train_rowptr), _ptr(train_col), int(n_items),
+                                    int(seed) & (2**64 - 1), int(epoch) & (2**64 - 1), int(begin), int(count), _ptr(out[0]), _ptr(out[1]),
+                                    _ptr(out[2]), _ptr(n_exhausted), _stream(dev))
+    _lib.check(rc, "cr_sample_pairwise")
+    return out[0, :count], out[1, :count], out[2, :count]

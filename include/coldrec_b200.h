@@ -125,6 +125,11 @@ CR_API int cr_score_topk_f32(const float *user_tab, const int32_t *user_ids, int
 CR_API int cr_debug_tc_tile(const float *user_tab, int64_t n_q, const float *item_tab, int64_t n_items, int K,
                             float *out_score, int32_t *out_id, float *dbg, void *workspace, size_t ws_bytes, void *stream);
 
+/* Diagnostic: with the environment variable CR_TC_DEBUG_MODE=8 the tcgen05 sweep stamps %globaltimer at fixed points
+ * of every unit (16 uint64 slots per unit: entry, setup, queries in TMEM, after tile 0/15/127/1023/4095/8191/last, exit);
+ * this copies the stamps of the first n_units (<= 8192) units of the last sweep to HOST memory. */
+CR_API int cr_debug_tc_timeline(unsigned long long *host_out, int n_units);
+
 /* Merge G candidate lists per query (item shards / ALDI's two item groups, model/ALDI.py:149-160 /
  * per-GPU candidates after the NCCL allgather) into one top-K by (score desc, id asc).
  * in_score/in_id: [G, n_q, K] (list g of query j at ((g*n_q)+j)*K); ids < 0 are padding. */
@@ -175,6 +180,46 @@ CR_API int cr_bn_fold_f32(const float *gamma, const float *beta, const float *me
 /* out = Vin*keep + tanh(sum_g gate[:,g] * expert) * one_minus_keep   (model/Heater.py:189-198) */
 CR_API int cr_heater_blend_f32(const float *gate, int n_expert, const float *expert, const float *Vin, float keep,
                         float one_minus_keep, int64_t n_rows, int d, float *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5 — fused BPR training step for the propagated tables.
+ * Replaces, per mini-batch of model/LightGCN.py:21-28 (same loop in MF / SimGCL / NGCF / KNN ...):
+ *     u_e, p_e, n_e = rec_user_emb[u_idx], rec_item_emb[i_idx], rec_item_emb[j_idx]             (:24)
+ *     loss = bpr_loss(u_e, p_e, n_e) + l2_reg_loss(reg, u_e, p_e, n_e)        (util/utils.py:25-29, 43-47)
+ *     loss.backward()                       (the scatter-add gradients of the three row gathers)
+ *   bpr  = mean_b -log(1e-5 + sigmoid(<u,p> - <u,n>)),  regl = reg * (|U_b|_F + |P_b|_F + |N_b|_F) / B
+ *   loss[0..2] = bpr + regl, bpr, regl (device fp32[4]);
+ *   grad_user[u,:] / grad_item[i,:] += d loss / d row  (dense (n_users,d) / (n_items,d) tables the caller zeroed;
+ *   rows that occur several times in the batch accumulate; fp32 vector reductions, order unspecified).
+ * The backward of the propagation is cr_spmm_csr_f32 applied to these gradient tables: the normalised
+ * adjacency is symmetric (util/databuilder.py:236-248), so d loss / d E0 = mean_k A^k . grad.
+ * ------------------------------------------------------------------------------------------------ */
+CR_API size_t cr_bpr_workspace_bytes(int64_t batch);
+CR_API int cr_bpr_fwd_bwd_f32(const float *user_emb, const float *item_emb, int d, const int32_t *u_idx, const int32_t *i_idx,
+                              const int32_t *j_idx, int64_t batch, float reg, float *loss, float *grad_user, float *grad_item,
+                              void *workspace, size_t ws_bytes, void *stream);
+
+/* torch.optim.Adam(lr, betas, eps) single-tensor update (model/LightGCN.py:16 + optimizer.step() :28), no weight
+ * decay / amsgrad; `step` is the 1-based step count; the gradient is read as grad * grad_scale.
+ *   m += (g - m)(1 - beta1);  v = v beta2 + (1 - beta2) g g;  p -= lr/(1 - beta1^t) * m / (sqrt(v)/sqrt(1 - beta2^t) + eps) */
+CR_API int cr_adam_step_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, double lr,
+                            double beta1, double beta2, double eps, int64_t step, float grad_scale, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K6 — pairwise (user, positive, negative) sampler.
+ * Replaces next_batch_pairwise (util/utils.py:123-157): the batch [begin, begin+count) of one epoch's shuffled
+ * training pairs, each with one negative item drawn uniformly from [0, n_items) and re-drawn while it is one of
+ * the user's training items (train CSR: train_rowptr int64 [n_users+1], train_col int32 ascending per row —
+ * the scorer's mask CSR over all users).  The epoch permutation is a keyed bijection of [0, n_pairs) evaluated
+ * per index (6-round Feistel network, cycle-walked), the draws are Philox4x32-10 words keyed by (seed, epoch)
+ * with counter (position, attempt): batches are reproducible and independent of launch geometry.
+ * n_exhausted (device int32, nullable, caller-zeroed) counts samples that still collided after 4096 draws
+ * (a user who interacted with nearly every item; the reference loops forever there).
+ * ------------------------------------------------------------------------------------------------ */
+CR_API int cr_sample_pairwise(const int32_t *pair_user, const int32_t *pair_item, int64_t n_pairs,
+                              const int64_t *train_rowptr, const int32_t *train_col, int32_t n_items, uint64_t seed,
+                              uint64_t epoch, int64_t begin, int64_t count, int32_t *out_user, int32_t *out_pos,
+                              int32_t *out_neg, int32_t *n_exhausted, void *stream);
 
 #ifdef __cplusplus
 }

@@ -3,7 +3,8 @@
 
 TEST INFRASTRUCTURE ONLY.  Run in the build container (the reference tree is not on the GPU box):
 
-    python oracle/make_golden.py            # writes tests/golden/{eval_item,eval_user,eval_tiny,graph,towers}.npz
+    python oracle/make_golden.py            # writes tests/golden/{eval_item,eval_user,eval_tiny,graph,towers,train}.npz
+    python oracle/make_golden.py --only train   # just one of them
 
 What is executed from the reference, unmodified: ``data/split.py`` + ``data/convert.py`` (subprocess),
 ``util.loader.DataLoader``, ``util.databuilder.ColdStartDataBuilder`` / ``TorchGraphInterface``,
@@ -11,7 +12,8 @@ What is executed from the reference, unmodified: ``data/split.py`` + ``data/conv
 ``model.MF`` / ``model.ALDI`` / ``model.VBPR``, ``util.evaluator.ranking_evaluation``,
 ``model.LightGCN.LGCN_Encoder``, ``model.SimGCL.SimGCL_Encoder``, ``model.NGCF.NGCF_Encoder``,
 ``model.DropoutNet.DropoutNet_Learner``, ``model.Heater.Heater_Learner``, ``model.GAR.GAR_Learner``,
-``model.ALDI.ALDI_Learner``.  A stub ``faiss`` module is injected because ``model/__init__.py``
+``model.ALDI.ALDI_Learner``; for train.npz the training loop body of ``model/LightGCN.py:21-28`` / ``model/MF.py:19-27``
+(``util.utils.next_batch_pairwise``, ``bpr_loss``, ``l2_reg_loss``, ``torch.optim.Adam``).  A stub ``faiss`` module is injected because ``model/__init__.py``
 imports KNN/NCL which import faiss (absent here).  Inputs are seeded; fixtures stay small.
 """
 import argparse
@@ -225,6 +227,53 @@ def golden_graph(data, seed):
     return out
 
 
+def golden_train(data, seed, n_steps=3, bs=256, lr=5e-3, reg=1e-2):
+    """The loop body of LightGCN.train / MF.train (model/LightGCN.py:21-28, model/MF.py:19-27) for a few batches:
+    the reference's own sampler, encoder, losses and torch.optim.Adam.  lr / reg are larger than the CLI defaults
+    so that three steps move the tables well above fp32 noise."""
+    from model.LightGCN import LGCN_Encoder
+    from model.MF import Matrix_Factorization
+    from util.utils import next_batch_pairwise, bpr_loss, l2_reg_loss
+    out = dict(lr=np.array(lr), reg=np.array(reg), bs=np.array(bs), n_steps=np.array(n_steps),
+               train_u=np.array([data.user[p[0]] for p in data.training_data], dtype=np.int64),
+               train_i=np.array([data.item[p[1]] for p in data.training_data], dtype=np.int64),
+               n_item_table=np.array(len(data.item)))
+    # one full epoch of the reference sampler (np.random state seeded): every batch, for the sampler property tests
+    np.random.seed(seed)
+    saved = list(data.training_data)
+    batches = [tuple(np.asarray(x, dtype=np.int64) for x in b) for b in next_batch_pairwise(data, bs)]
+    data.training_data[:] = saved                         # the sampler shuffles the list in place (util/utils.py:125)
+    out["epoch_u"] = np.concatenate([b[0] for b in batches]); out["epoch_i"] = np.concatenate([b[1] for b in batches])
+    out["epoch_j"] = np.concatenate([b[2] for b in batches])
+    for tag, make in (("lgcn", lambda: LGCN_Encoder(data, D, 3, torch.device("cpu"))), ("mf", lambda: Matrix_Factorization(data, D))):
+        torch.manual_seed(seed)
+        model = make()
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=lr)
+        out[f"{tag}_E0_user"] = model.embedding_dict["user_emb"].detach().numpy().copy()
+        out[f"{tag}_E0_item"] = model.embedding_dict["item_emb"].detach().numpy().copy()
+        for s in range(n_steps):
+            user_idx, pos_idx, neg_idx = (b.tolist() for b in batches[s])
+            rec_user_emb, rec_item_emb = model()
+            user_emb, pos_item_emb, neg_item_emb = rec_user_emb[user_idx], rec_item_emb[pos_idx], rec_item_emb[neg_idx]
+            bl, rl = bpr_loss(user_emb, pos_item_emb, neg_item_emb), l2_reg_loss(reg, user_emb, pos_item_emb, neg_item_emb)
+            batch_loss = bl + rl
+            opt.zero_grad()
+            batch_loss.backward()
+            opt.step()
+            out[f"{tag}_loss{s}"] = np.array([batch_loss.item(), bl.item(), rl.item()], dtype=np.float64)
+            out[f"{tag}_grad{s}_user"] = model.embedding_dict["user_emb"].grad.numpy().copy()
+            out[f"{tag}_grad{s}_item"] = model.embedding_dict["item_emb"].grad.numpy().copy()
+            out[f"{tag}_param{s}_user"] = model.embedding_dict["user_emb"].detach().numpy().copy()
+            out[f"{tag}_param{s}_item"] = model.embedding_dict["item_emb"].detach().numpy().copy()
+        for name, key in (("user", "user_emb"), ("item", "item_emb")):
+            st = opt.state[model.embedding_dict[key]]
+            out[f"{tag}_exp_avg_{name}"], out[f"{tag}_exp_avg_sq_{name}"] = st["exp_avg"].numpy().copy(), st["exp_avg_sq"].numpy().copy()
+    for s in range(n_steps):
+        out[f"batch{s}_u"], out[f"batch{s}_i"], out[f"batch{s}_j"] = batches[s]
+    return out
+
+
 def _randomise_bn(module, g):
     for m in module.modules():
         if isinstance(m, torch.nn.BatchNorm1d):
@@ -299,11 +348,17 @@ def golden_towers(work, name, data, user_emb, item_emb, seed):
 
 
 def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None, choices=[None, "train"], help="regenerate a single fixture")
+    only = ap.parse_args().only
     _import_reference()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)           # fixtures must not depend on thread-count-dependent blocking
     with tempfile.TemporaryDirectory() as work:
         ev, data = golden_eval(work, "synitem", "item", 11, n_users=150, n_items=240, n_inter=4200, content_dim=24)
+        np.savez_compressed(os.path.join(OUT, "train.npz"), **golden_train(data, 14))
+        if only == "train":
+            return
         np.savez_compressed(os.path.join(OUT, "eval_item.npz"), **ev)
         np.savez_compressed(os.path.join(OUT, "graph.npz"), **golden_graph(data, 12))
         tw = golden_towers(work, "synitem", data, torch.from_numpy(ev["user_emb"]), torch.from_numpy(ev["item_emb"]), 13)
