@@ -47,6 +47,10 @@ def parse():
     ap.add_argument("--graph-edges", type=int, default=GRAPH_EDGES)
     ap.add_argument("--cpu-sample-users", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="items", choices=["items", "users"],
+                    help="N>1 scoring layout: item-sharded + candidate all-gather (north star, default) or user-sharded (no exchange)")
+    ap.add_argument("--no-train", action="store_true", help="skip the LightGCN training-step line of the lightgcn workload")
+    ap.add_argument("--train-batch", type=int, default=4096)
     return ap.parse_args()
 
 
@@ -149,7 +153,7 @@ def barrier(world, device):
 def run_b200(args):
     import coldrec_b200 as cr
     from coldrec_b200 import _lib, ops
-    from coldrec_b200.dist import ShardedFullRankScorer, shard_range
+    from coldrec_b200.dist import ShardedFullRankScorer, UserShardedFullRankScorer, shard_range
     from coldrec_b200.scoring import EvalPlan, HostBatchEvaluator
 
     rank, local_rank, world = dist_env()
@@ -169,12 +173,13 @@ def run_b200(args):
         n_q = args.users_per_step * world
         g = torch.Generator(device=device).manual_seed(1)
         user_tab = torch.randn(args.n_users, D, device=device, generator=g) * 0.125
-        ib, ie = shard_range(args.n_items, rank, world)
-        gi = torch.Generator(device=device).manual_seed(1000 + rank)
+        by_users = args.shard == "users" and world > 1
+        ib, ie = (0, args.n_items) if by_users else shard_range(args.n_items, rank, world)
+        gi = torch.Generator(device=device).manual_seed(1000 + (0 if by_users else rank))
         item_shard = torch.randn(ie - ib, D, device=device, generator=gi) * 0.125
         plans_d = make_step_plans(W + Ksteps, n_q, args.n_users, args.n_items, 6, device)
         plans = [EvalPlan.from_arrays(**p) for p in plans_d]
-        scorer = ShardedFullRankScorer(K, ops.SCORE_TF32_CHECKED)
+        scorer = (UserShardedFullRankScorer if by_users else ShardedFullRankScorer)(K, ops.SCORE_TF32_CHECKED)
 
         def step(plan):
             s, i = scorer.topk(user_tab, item_shard, ib, plan)
@@ -200,7 +205,8 @@ def run_b200(args):
         lib.cr_profile_enable(0)
         value = n_q * Ksteps / (ms * 1e-3)
         sweep_ms = tot.value / max(cnt.value, 1)
-        flops = 2.0 * n_q * (ie - ib) * D                       # algorithmic FLOPs of one sweep launch (this rank's shard)
+        n_q_rank = (lambda r: r[1] - r[0])(shard_range(n_q, rank, world)) if by_users else n_q
+        flops = 2.0 * n_q_rank * (ie - ib) * D                  # algorithmic FLOPs of one sweep launch (this rank's shard)
         tf32_peak = pk["bf16_tflops_sustained"] / 2.0             # TF32 dense = half the bf16 rate; kernel runs inside a long step
         achieved = flops / (sweep_ms * 1e-3) / 1e12 if sweep_ms > 0 else 0.0
         roofline = {"bound": "tensor", "kernel": "score_sweep_tc_kernel", "achieved": round(achieved, 1), "peak": round(tf32_peak, 1),
@@ -228,7 +234,8 @@ def run_b200(args):
                    config={"workload": f"C5 full-catalog top-{K} scoring: {args.n_users} users x {args.n_items} items, d={D}, "
                                        f"{n_q} users/step, ~{MASK_PER_USER} train-masked + {GT_PER_USER} gt items/user, "
                                        f"Recall/NDCG@{TOPN} on device",
-                           "parallelism": f"item-sharded x{world} + NCCL candidate all-gather" if world > 1 else "single GPU",
+                           "parallelism": (f"user-sharded x{world}, item table replicated, no candidate exchange" if by_users else
+                                           f"item-sharded x{world} + NCCL candidate all-gather") if world > 1 else "single GPU",
                            "l2": "inputs larger than L2 (item shard %.0f MB); no flush" % ((ie - ib) * D * 4 / 2**20),
                            "users_per_step": n_q, "n_items": args.n_items, "K": K},
                    e2e={"value": round(n_q * Ksteps / (e2e_ms * 1e-3), 1), "unit": "users/s", "h2d_bytes_per_step": hb.h2d_bytes,
@@ -343,7 +350,50 @@ def run_lightgcn(args, device, rank, world, pk, pk_src, lib):
                clocks=clk.summary())
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_spmm_baseline(G, E0u, E0i)
+    if world == 1 and not args.no_train:
+        out["train_step"] = run_train_step(args, device, G, E0u, E0i, pk, lib)
     return out
+
+
+def run_train_step(args, device, G, E0u, E0i, pk, lib):
+    """One LightGCN optimisation step (model/LightGCN.py:21-28) on the same graph: device sampler -> forward propagation ->
+    fused BPR loss + row gradients -> backward propagation (same SpMM, symmetric adjacency) -> Adam.  Reported next to the
+    propagation line; the sampled batch changes every step."""
+    import coldrec_b200 as cr
+    n_users, n_items = E0u.shape[0], E0i.shape[0]
+    N, nnz = n_users + n_items, G.nnz
+    # training pairs = the user->item half of the adjacency (one per stored interaction)
+    rp_u = G.rowptr[:n_users + 1]
+    pu = torch.repeat_interleave(torch.arange(n_users, device=device, dtype=torch.int32), (rp_u[1:] - rp_u[:-1]))
+    pi = (G.col[:int(rp_u[-1])] - n_users).to(torch.int32)
+    smp = cr.PairwiseSampler(pu, pi, n_users, n_items, seed=7)
+    del pu, pi
+    step = cr.BprTrainStep(G, E0u, E0i, LAYERS, 1e-3, 1e-4)
+    B, W, Ksteps = args.train_batch, max(args.warmup, 3), max(args.steps, 3)
+    buf = torch.empty((3, B), dtype=torch.int32, device=device)
+    def one(k):
+        u, i, j = smp.batch(0, (k * B) % max(smp.n_pairs - B, 1), B, out=buf)
+        return step.step(u, i, j)
+    for k in range(W):
+        one(k)
+    torch.cuda.synchronize(device)
+    l0 = lib.cr_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(W, W + Ksteps):
+        loss = one(k)
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / Ksteps
+    # algorithmic bytes: two propagations (SURVEY 8d per layer) + Adam (28 B/element) + gradient-table clear (4 B/element)
+    bytes_layer = nnz * (8 + 4 * D) + 3 * N * 4 * D + 8 * (N + 1)
+    step_bytes = 2 * LAYERS * bytes_layer + N * D * 32
+    return {"metric": "LightGCN training steps/sec (sample + forward + BPR + backward + Adam)", "value": round(1e3 / ms, 3), "unit": "steps/s",
+            "ms_per_step": round(ms, 3), "batch": B, "edges_per_s": round(2 * LAYERS * nnz / (ms * 1e-3), 1),
+            "gpu_launches": int(lib.cr_launch_count() - l0), "steps": Ksteps, "warmup": W,
+            "roofline": {"bound": "hbm", "achieved": round(step_bytes / (ms * 1e-3) / 1e9, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": round(step_bytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4), "bytes_per_step": step_bytes},
+            "loss": [round(x, 6) for x in loss.cpu().tolist()[:3]], "sampler_exhausted": int(smp.n_exhausted.item())}
 
 
 # ------------------------------------------------------------------------------------------- CPU arms (oracle port)

@@ -11,8 +11,9 @@ from .scoring import FLAG_COLD, FLAG_WARM, EvalPlan, FullRankScorer, item_flags_
 from .trainer import AldiScoreTables, BaseColdStartTrainer, FusedEvalMixin, TwoProductScoreTables
 from . import towers
 from .training import BprTrainStep, PairwiseSampler
+from .databuilder import ArrayDataBuilder
 
 __all__ = ["ops", "towers", "RecList", "ranking_evaluation", "CsrGraph", "bipartite_norm_csr", "propagate", "propagate_ngcf",
            "FLAG_COLD", "FLAG_WARM", "EvalPlan", "FullRankScorer", "item_flags_from", "AldiScoreTables",
            "BaseColdStartTrainer", "FusedEvalMixin", "TwoProductScoreTables", "PropagationBuffers", "propagate_table",
-           "BprTrainStep", "PairwiseSampler"]
+           "BprTrainStep", "PairwiseSampler", "ArrayDataBuilder"]

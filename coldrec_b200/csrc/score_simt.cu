@@ -23,7 +23,8 @@ constexpr int kIS = kKC + 4;         // padded item-tile row stride (floats): co
 constexpr int kCap = CR_MAX_K + kTI; // candidate buffer entries per query
 constexpr int kThreads = 256;
 constexpr int kMaxSplits = 32;
-constexpr int kMaxD = 256;
+constexpr int kMaxD = 256;            // widest table whose query vectors stay resident in shared memory; wider ones are
+                                     // streamed k-chunk by k-chunk next to the item tile (content kNN: d = 300 .. 2740)
 
 struct Cand {
     float s;
@@ -65,11 +66,13 @@ __device__ void compact_query(Cand* buf, int* cnt, float* thr, Cand* tmp, int K,
     __syncwarp();
 }
 
+template <bool RESIDENT>
 __global__ void __launch_bounds__(kThreads) score_topk_exact_kernel(const ScoreParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int d = p.d;
-    float* s_user = reinterpret_cast<float*>(smem_raw);              // [kTU][d]
-    float* s_item = s_user + kTU * d;                                // [kTI][kIS]
+    const int ustride = RESIDENT ? d : kKC;                          // floats per query row held in shared memory
+    float* s_user = reinterpret_cast<float*>(smem_raw);              // [kTU][d] (resident) or [kTU][kKC] (streamed)
+    float* s_item = s_user + kTU * ustride;                          // [kTI][kIS]
     Cand* s_buf = reinterpret_cast<Cand*>(s_item + kTI * kIS);       // [kTU][kCap]
     Cand* s_tmp = s_buf + kTU * kCap;                                // [8 warps][CR_MAX_K]
     float* s_thr = reinterpret_cast<float*>(s_tmp + 8 * CR_MAX_K);   // [kTU]
@@ -96,7 +99,7 @@ __global__ void __launch_bounds__(kThreads) score_topk_exact_kernel(const ScoreP
     }
     __syncthreads();
     // stage the query vectors (gathered through user_ids)
-    for (int i = tid; i < kTU * (d / 4); i += kThreads) {
+    for (int i = tid; RESIDENT && i < kTU * (d / 4); i += kThreads) {
         const int u = i / (d / 4), c = i % (d / 4);
         const int q = s_q[u];
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -125,13 +128,25 @@ __global__ void __launch_bounds__(kThreads) score_topk_exact_kernel(const ScoreP
                 if (it < it_end && c < kc4) v = __ldg(reinterpret_cast<const float4*>(p.item_tab + it * d + k0) + c);
                 reinterpret_cast<float4*>(s_item + r * kIS)[c] = v;
             }
+            if (!RESIDENT) {        // this k-chunk of the 32 query vectors (re-read per item tile: L2 resident, 4 KB)
+                for (int i = tid; i < kTU * (kKC / 4); i += kThreads) {
+                    const int u = i / (kKC / 4), c = i % (kKC / 4);
+                    const int q = s_q[u];
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (q >= 0 && c < kc4) {
+                        const int64_t row = p.user_ids ? (int64_t)p.user_ids[q] : (int64_t)q;
+                        v = __ldg(reinterpret_cast<const float4*>(p.user_tab + row * d + k0) + c);
+                    }
+                    reinterpret_cast<float4*>(s_user + u * kKC)[c] = v;
+                }
+            }
             __syncthreads();
 #pragma unroll
             for (int kk = 0; kk < kKC; kk += 4) {
                 if (k0 + kk < d) {
                     float4 uu[4], ii[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) uu[u] = *reinterpret_cast<const float4*>(s_user + (ug + u) * d + k0 + kk);
+                    for (int u = 0; u < 4; ++u) uu[u] = *reinterpret_cast<const float4*>(s_user + (ug + u) * ustride + (RESIDENT ? k0 : 0) + kk);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) ii[i] = *reinterpret_cast<const float4*>(s_item + (lane + 32 * i) * kIS + kk);
 #pragma unroll
@@ -194,7 +209,7 @@ __global__ void __launch_bounds__(kThreads) score_topk_exact_kernel(const ScoreP
 }
 
 size_t exact_smem_bytes(int d) {
-    return (size_t)kTU * d * 4 + (size_t)kTI * kIS * 4 + (size_t)kTU * kCap * sizeof(Cand) + 8 * CR_MAX_K * sizeof(Cand) +
+    return (size_t)kTU * (d <= kMaxD ? d : kKC) * 4 + (size_t)kTI * kIS * 4 + (size_t)kTU * kCap * sizeof(Cand) + 8 * CR_MAX_K * sizeof(Cand) +
            kTU * 4 * 3;
 }
 
@@ -316,7 +331,6 @@ int launch_merge(const float* in_score, const int32_t* in_id, int G, int64_t n_q
 
 static int launch_exact_impl(const ExactJob& j, const RefineList* rl, int S, int64_t n_sweep, int compact, int64_t gate_lo,
                              int64_t gate_hi, void* ws, size_t ws_bytes, cudaStream_t st) {
-    if (j.d > kMaxD) return CR_ERR_UNSUPPORTED;
     if (n_sweep == 0) return CR_OK;
     ScoreParams p{j.user_tab, j.user_ids, j.n_q, j.item_tab, j.item_gids, j.item_id_base, j.n_items, j.d, j.mask_rowptr,
                   j.mask_col, j.item_flags, j.flag_exclude, rl ? rl->list : nullptr, rl ? rl->count : nullptr, gate_lo, gate_hi,
@@ -336,10 +350,15 @@ static int launch_exact_impl(const ExactJob& j, const RefineList* rl, int S, int
         p.out_id = part_i;
     }
     const size_t smem = exact_smem_bytes(j.d);
-    CR_CUDA_TRY(cudaFuncSetAttribute(score_topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t gx = (n_sweep + kTU - 1) / kTU;
     if (gx > 0x7fffffffLL) return CR_ERR_UNSUPPORTED;
-    score_topk_exact_kernel<<<dim3((unsigned)gx, (unsigned)S), kThreads, smem, st>>>(p);
+    if (j.d <= kMaxD) {
+        CR_CUDA_TRY(cudaFuncSetAttribute(score_topk_exact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        score_topk_exact_kernel<true><<<dim3((unsigned)gx, (unsigned)S), kThreads, smem, st>>>(p);
+    } else {
+        CR_CUDA_TRY(cudaFuncSetAttribute(score_topk_exact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        score_topk_exact_kernel<false><<<dim3((unsigned)gx, (unsigned)S), kThreads, smem, st>>>(p);
+    }
     CR_LAUNCH_CHECK("score_topk_exact_kernel");
     if (S > 1) {
         RefineList sub{rl ? rl->list : nullptr, rl ? rl->count : nullptr, n_sweep};

@@ -99,6 +99,20 @@ class ShardedFullRankScorer:
         return metrics_from_sums(sums.cpu().numpy(), plan.n_q, Ns, rounded)
 
 
+class UserShardedFullRankScorer(ShardedFullRankScorer):
+    """User-sharded full ranking: the item table is replicated (2.56 GB at 10M x 64) and every GPU ranks its slice of the
+    eval users against the WHOLE catalogue — no candidate exchange at all, only the metric all-reduce.  Same interface
+    as ``ShardedFullRankScorer`` (``topk`` takes the full table with ``item_begin = 0``).  The north-star layout is the
+    item-sharded one; this is the zero-communication alternative of SURVEY §8(e): each GPU runs the long sweep (10M
+    items per 256-query unit) where the fused kernel is at its best, instead of W times as many short ones."""
+
+    def topk(self, user_tab, item_table: torch.Tensor, item_begin: int, plan: EvalPlan, item_flags=None):
+        if item_begin != 0:
+            raise ValueError("user-sharded scoring takes the whole item table (item_begin must be 0)")
+        lo, hi = self.user_slice(plan.n_q) if self.world > 1 else (0, plan.n_q)
+        return self._local_topk(user_tab, item_table, 0, plan.slice(lo, hi) if self.world > 1 else plan, item_flags)
+
+
 class RowPartitionedGraph:
     """A square adjacency split by rows over the ranks of ``group`` with padded node numbering.
 

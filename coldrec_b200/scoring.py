@@ -78,6 +78,16 @@ class EvalPlan:
         t = lambda a: torch.from_numpy(a).to(device)
         return cls(users, t(uids), t(mrp), t(mc), t(grp), t(gc), flag_exclude_for(cold_object, data_type))
 
+    def slice(self, lo: int, hi: int) -> "EvalPlan":
+        """Eval users [lo, hi) as a plan of their own (user-sharded scoring: every GPU ranks its slice of the users)."""
+        def rows(rowptr, col):
+            b, e = int(rowptr[lo]), int(rowptr[hi])
+            return (rowptr[lo:hi + 1] - b).contiguous(), col[b:e].contiguous()
+        mrp, mc = rows(self.mask_rowptr, self.mask_col)
+        grp, gc = rows(self.gt_rowptr, self.gt_col)
+        return EvalPlan(None if self.users is None else self.users[lo:hi], self.user_ids[lo:hi].contiguous(), mrp, mc, grp, gc,
+                        self.flag_exclude)
+
     @classmethod
     def from_arrays(cls, user_ids, mask_rowptr, mask_col, gt_rowptr, gt_col, flag_exclude=0, users=None) -> "EvalPlan":
         return cls(users if users is not None else None, user_ids, mask_rowptr, mask_col, gt_rowptr, gt_col, int(flag_exclude))

@@ -1,0 +1,109 @@
+"""CPU: the array-based data builder against the reference's ColdStartDataBuilder — through the golden
+id tables the reference produced (tests/golden/eval_*.npz) and through the oracle's line-by-line restatement of it."""
+import numpy as np
+import pytest
+
+from coldrec_b200.databuilder import ArrayDataBuilder
+from oracle import coldrec_oracle as O
+from tests.helpers import builder_args, load_golden
+
+
+@pytest.mark.parametrize("name", ["eval_item", "eval_user", "eval_tiny"])
+def test_id_tables_match_the_reference(name):
+    g = load_golden(name)
+    data = ArrayDataBuilder(*builder_args(g))
+    assert [data.id2user[i] for i in range(len(data.user))] == g["id2user"].tolist()
+    assert [data.id2item[i] for i in range(len(data.item))] == g["id2item"].tolist()
+    for k in ("mapped_cold_item_idx", "mapped_warm_item_idx", "mapped_cold_user_idx", "mapped_warm_user_idx"):
+        assert np.array_equal(np.asarray(getattr(data, k)), g[k]), k
+    gg = load_golden("graph") if name == "eval_item" else None
+    if gg is not None:      # the reference's own adjacency
+        adj = data.norm_adj.tocsr(); adj.sort_indices()
+        assert np.array_equal(adj.indptr, gg["adj_indptr"]) and np.array_equal(adj.indices, gg["adj_indices"])
+        assert np.allclose(adj.data, gg["adj_data"], rtol=1e-6, atol=0)
+        assert np.array_equal(data.train_user, gg["train_u"]) and np.array_equal(data.train_item, gg["train_i"])
+
+
+def _random_args(seed, n_users=60, n_items=45, n_inter=900, with_content=True):
+    rng = np.random.default_rng(seed)
+    raw_u = rng.permutation(500)[:n_users] + 7          # sparse, unordered raw ids
+    raw_i = rng.permutation(400)[:n_items] + 3
+    pairs = np.stack([raw_u[rng.integers(0, n_users, n_inter)], raw_i[rng.integers(0, n_items, n_inter)]], 1)   # with duplicates
+    cut = np.cumsum([0.6, 0.07, 0.07, 0.06, 0.06, 0.07])
+    parts = np.split(pairs, (cut * n_inter).astype(int))
+    rows = [[[int(u), int(i), float(1 + (k % 3))] for k, (u, i) in enumerate(p)] for p in parts]
+    train, wv, wt, cv, ct, ov, ot = rows
+    seen_u = sorted({r[0] for p in rows for r in p}); seen_i = sorted({r[1] for p in rows for r in p})
+    half_u, half_i = len(seen_u) // 2, len(seen_i) // 2
+    ucont = rng.standard_normal((520, 5)) if with_content else None
+    icont = rng.standard_normal((420, 4)) if with_content else None
+    return (train, wv, cv, ov, wt, ct, ot, len(seen_u) + 3, len(seen_i) + 2, seen_u[:half_u], seen_i[:half_i], seen_u[half_u:],
+            seen_i[half_i:], ucont, icont)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_equals_the_restated_reference_builder(seed):
+    args = _random_args(seed)
+    ref, got = O.OracleData(*args), ArrayDataBuilder(*args)
+    assert got.user == ref.user and got.item == ref.item
+    assert got.id2user == ref.id2user and got.id2item == ref.id2item
+    for k in ("mapped_cold_item_idx", "mapped_warm_item_idx", "mapped_cold_user_idx", "mapped_warm_user_idx"):
+        assert np.array_equal(getattr(got, k), getattr(ref, k))
+    for k in ("training_set_u", "training_set_i", "warm_valid_set", "warm_test_set", "cold_valid_set", "cold_test_set",
+              "overall_valid_set", "overall_test_set"):
+        a, b = getattr(got, k), getattr(ref, k)
+        assert {u: dict(v) for u, v in a.items()} == {u: dict(v) for u, v in b.items()}, k
+        assert list(a.keys()) == list(b.keys()), k             # eval-user order is the dict order (BaseRecommender.py:115)
+    assert (got.ui_adj != ref.ui_adj).nnz == 0
+    d = (got.norm_adj - ref.norm_adj)
+    assert abs(d).max() <= 1e-7
+    n_u, n_i = len(ref.user), len(ref.item)
+    assert np.array_equal(got.mapped_user_content[:n_u], ref.mapped_user_content[:n_u])
+    assert np.array_equal(got.mapped_item_content[:n_i], ref.mapped_item_content[:n_i])
+    assert got.get_user_id(ref.id2user[3]) == 3 and got.get_item_id(ref.id2item[5]) == 5
+
+
+@pytest.mark.parametrize("split", ["warm_test", "cold_test", "overall_valid"])
+def test_eval_arrays_equal_the_per_user_construction(split):
+    args = _random_args(5)
+    ref, got = O.OracleData(*args), ArrayDataBuilder(*args)
+    a = got.eval_arrays(split)
+    gt = getattr(ref, f"{split}_set")
+    users = list(gt.keys())
+    assert a["users"].tolist() == users
+    assert a["user_ids"].tolist() == [ref.user[u] for u in users]
+    for j, u in enumerate(users):
+        want_mask = sorted(ref.item[i] for i in ref.training_set_u[u]) if u in ref.training_set_u else []
+        want_gt = sorted(ref.item[i] for i in gt[u])
+        assert a["mask_col"][a["mask_rowptr"][j]:a["mask_rowptr"][j + 1]].tolist() == want_mask
+        assert a["gt_col"][a["gt_rowptr"][j]:a["gt_rowptr"][j + 1]].tolist() == want_gt
+
+
+def test_train_csr_flags_sets_and_errors():
+    args = _random_args(9, with_content=False)
+    ref, got = O.OracleData(*args), ArrayDataBuilder(*args)
+    rowptr, col = got.train_csr()
+    m = got.interaction_mat.tocsr(); m.sum_duplicates(); m.sort_indices()
+    assert np.array_equal(rowptr[:m.shape[0] + 1], m.indptr) and np.array_equal(col, m.indices)
+    flags = got.item_flags()
+    assert set(np.nonzero(flags & 1)[0]) == set(ref.mapped_cold_item_idx.tolist())
+    assert set(np.nonzero(flags & 2)[0]) == set(ref.mapped_warm_item_idx.tolist())
+    uid_sets = got.training_set_uid
+    for u, uid in ref.user.items():
+        assert uid_sets[uid] == set(ref.training_set_u[u]) if u in ref.training_set_u else uid_sets[uid] == set()
+    assert got.training_size() == (len(ref.training_set_u), len(ref.training_set_i), len(args[0]))
+    with pytest.raises(Exception, match="user 99999 not in current id table"):
+        got.get_user_id(99999)
+    with pytest.raises(Exception, match="item 12345 not in current id table"):
+        got.get_item_id_list([args[0][0][1], 12345])
+
+
+def test_accepts_arrays_and_empty_splits():
+    args = list(_random_args(3, with_content=False))
+    as_arrays = [np.asarray([(r[0], r[1]) for r in a], dtype=np.int64).reshape(-1, 2) for a in args[:7]]
+    a, b = ArrayDataBuilder(*args), ArrayDataBuilder(*as_arrays, *args[7:])
+    assert a.user == b.user and a.item == b.item and np.array_equal(a.train_csr()[1], b.train_csr()[1])
+    args[2] = []                     # no cold-valid interactions at all
+    c = ArrayDataBuilder(*args)
+    e = c.eval_arrays("cold_valid")
+    assert len(e["user_ids"]) == 0 and e["mask_rowptr"].tolist() == [0] and e["gt_rowptr"].tolist() == [0]

@@ -55,7 +55,7 @@ def _worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from coldrec_b200.dist import RowPartitionedGraph, ShardedFullRankScorer, shard_range
+        from coldrec_b200.dist import RowPartitionedGraph, ShardedFullRankScorer, UserShardedFullRankScorer, shard_range
         from coldrec_b200.scoring import EvalPlan
         c = _case()
         K = c["K"]
@@ -65,8 +65,9 @@ def _worker(rank, world, port, ret):
             # exact (score desc, id asc) local list from oracle scores of this shard
             n_loc = item_tab.shape[0]
             s = (user_tab[plan.user_ids.long()] @ item_tab.T).numpy().copy()
+            prp, pcol = plan.mask_rowptr.numpy(), plan.mask_col.numpy()
             for j in range(plan.n_q):
-                m = c["col"][c["rowptr"][j]:c["rowptr"][j + 1]] - item_begin
+                m = pcol[prp[j]:prp[j + 1]] - item_begin
                 s[j, m[(m >= 0) & (m < n_loc)]] = O.MASK_SENTINEL
             ids = np.broadcast_to(np.arange(item_begin, item_begin + n_loc, dtype=np.int32), s.shape)
             ts, ti = _sorted_topk(s, ids, K)
@@ -97,6 +98,9 @@ def _worker(rank, world, port, ret):
         s, i = sc.topk(Ut, It[b:e], b, plan)
         perf = sc.metrics(i, plan, [10, 20], rounded=False)
         lo, hi = sc.user_slice(plan.n_q)
+        usc = UserShardedFullRankScorer(K, group=None, local_topk=local_topk, merge=merge, metrics=metrics)
+        us, ui = usc.topk(Ut, It, 0, plan)
+        uperf = usc.metrics(ui, plan, [10, 20], rounded=False)
 
         adj = O.normalize_graph_mat(O.bipartite_adjacency(c["eu"], c["ei"], c["n_users"], c["n_items"])).tocsr()
         adj.sort_indices()
@@ -120,7 +124,7 @@ def _worker(rank, world, port, ret):
             out[ego] = G.propagate(E0, 3, include_ego=ego).numpy()
         out["seg"] = G2.propagate(E0, 3).numpy()
         ret[rank] = dict(s=s.numpy(), i=i.numpy(), lo=lo, hi=hi, perf=perf, prop=out, bounds=G.bounds, parts=G2.parts,
-                         rows_pad=G2.rows_pad)
+                         rows_pad=G2.rows_pad, us=us.numpy(), ui=ui.numpy(), uperf=uperf)
     finally:
         dist.destroy_process_group()
 
@@ -145,11 +149,14 @@ def test_sharded_scoring_and_partitioned_propagation_world2():
         lo, hi = ret[r]["lo"], ret[r]["hi"]
         assert np.array_equal(ret[r]["i"], ti[lo:hi]), "sharded ids must equal the single sweep bit for bit"
         assert np.allclose(ret[r]["s"], ts[lo:hi], atol=1e-6)
+        assert np.array_equal(ret[r]["ui"], ti[lo:hi]), "user-sharded ids must equal the single sweep as well"
+        assert np.allclose(ret[r]["us"], ts[lo:hi], atol=1e-6)
         covered += hi - lo
     assert covered == len(c["uids"])
     want = O.metrics_from_topk(ti.astype(np.int64), c["gt_rowptr"], c["gt_col"].astype(np.int64), [10, 20])
     for r in range(world):
         assert np.allclose(ret[r]["perf"], want, atol=1e-9), "all-reduced metrics must equal the global ones on every rank"
+        assert np.allclose(ret[r]["uperf"], want, atol=1e-9)
     adj = O.normalize_graph_mat(O.bipartite_adjacency(c["eu"], c["ei"], c["n_users"], c["n_items"]))
     for ego in (True, False):
         ru, ri = O.propagate(adj, Ut, It, 3, include_ego=ego)
