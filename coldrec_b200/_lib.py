@@ -49,7 +49,8 @@ SIGNATURES = {
     "cr_heater_blend_f32": (c_int, [_P, c_int, _P, _P, c_float, c_float, c_int64, c_int, _P, _P]),
     "cr_bpr_workspace_bytes": (c_size_t, [c_int64]),
     "cr_bpr_fwd_bwd_f32": (c_int, [_P, _P, c_int, _P, _P, _P, c_int64, c_float, _P, _P, _P, _P, c_size_t, _P]),
-    "cr_adam_step_f32": (c_int, [_P, _P, _P, _P, c_int64, c_double, c_double, c_double, c_double, c_int64, c_float, _P]),
+    "cr_adam_step_f32": (c_int, [_P, _P, _P, _P, c_int64, c_double, c_double, c_double, c_double, c_int64, c_float, _P, _P]),
+    "cr_adam_scalars": (c_int, [c_double, c_double, c_double, c_int64, ctypes.POINTER(c_float)]),
     "cr_sample_pairwise": (c_int, [_P, _P, c_int64, _P, _P, c_int32, ctypes.c_uint64, ctypes.c_uint64, c_int64, c_int64, _P, _P, _P,
                                    _P, _P]),
 }

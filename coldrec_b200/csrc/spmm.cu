@@ -14,9 +14,14 @@
 
 namespace {
 
-constexpr int kLongRow = 512;
-constexpr int kChunk = 512;
+constexpr int kLongRow = 512;       // graphs of >= kSmallNnz nonzeros: rows longer than this take the split path ...
+constexpr int kChunk = 512;         // ... in chunks of this many nonzeros
+constexpr int kSmallNnz = 1 << 23;  // dataset-sized graphs (MovieLens / CiteULike / XING: 10^5 .. 10^6.5 nonzeros) are latency
+constexpr int kSmallLongRow = 64;   // bound: a 500-nonzero row walked by one 8-lane group is the whole kernel's critical path
+constexpr int kSmallChunk = 64;     // there, so they split at 64 nonzeros and spread the chunks over the idle SMs
 constexpr int kThreads = 256;
+inline int long_row_of(int64_t nnz) { return nnz >= kSmallNnz ? kLongRow : kSmallLongRow; }
+inline int chunk_of(int64_t nnz) { return nnz >= kSmallNnz ? kChunk : kSmallChunk; }
 
 struct PlanHeader {
     int n_chunks;
@@ -43,8 +48,8 @@ struct PlanLayout {
 
 PlanLayout plan_layout(int64_t nnz, int d) {
     PlanLayout L;
-    L.max_long = nnz / (kLongRow + 1) + 1;
-    L.max_chunks = nnz / kChunk + L.max_long + 1;
+    L.max_long = nnz / (long_row_of(nnz) + 1) + 1;
+    L.max_chunks = nnz / chunk_of(nnz) + L.max_long + 1;
     L.off_long = 256;
     L.off_chunks = cr::align_up(L.off_long + (size_t)L.max_long * sizeof(LongRow), 256);
     L.off_partial = cr::align_up(L.off_chunks + (size_t)L.max_chunks * sizeof(Chunk), 256);
@@ -181,10 +186,9 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
 template <int LPR, int NV, bool HAS_VAL>
 __global__ void __launch_bounds__(kThreads, 3)
 spmm_rows_grouped_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
-                         int64_t n_rows, const float4* __restrict__ X4, const Epi ep, int long_row) {
+                         int64_t n_rows, const float4* __restrict__ X4, const Epi ep, int long_row, int kRowsPerWarp) {
     constexpr int RPW = 32 / LPR;     // rows in flight per warp
     constexpr int U = 4;              // gathers issued back to back per group
-    constexpr int kRowsPerWarp = 128;
     constexpr int d4 = LPR * NV;
     const int lane = threadIdx.x & 31, grp = lane / LPR, sub = lane % LPR;
     const int64_t row0 = (((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5) * kRowsPerWarp;
@@ -258,7 +262,7 @@ spmm_rows_grouped_kernel(const int64_t* __restrict__ rowptr, const int32_t* __re
 }
 
 __global__ void spmm_plan_kernel(const int64_t* __restrict__ rowptr, int64_t n_rows, PlanHeader* hdr, LongRow* long_rows,
-                                 Chunk* chunks, int max_long, int max_chunks) {
+                                 Chunk* chunks, int max_long, int max_chunks, int kLongRow, int kChunk) {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n_rows) return;
     const int64_t s = rowptr[row], len = rowptr[row + 1] - s;
@@ -324,24 +328,28 @@ struct SpmmArgs {
     Epi ep;
     PlanHeader* hdr; LongRow* long_rows; Chunk* chunks; float4* partial4;
     cudaStream_t stream;
+    int long_row;
 };
 
 template <int LPR, int NV, bool BOUNDS, int GLPR = 0, int GNV = 0>
 int launch_spmm(const SpmmArgs& a) {
-    const int long_row = a.hdr ? kLongRow : 0x7fffffff;
+    const int long_row = a.hdr ? a.long_row : 0x7fffffff;
     const int64_t blocks = (a.n_rows * 32 + kThreads - 1) / kThreads;
     if (blocks > 0x7fffffffLL) return CR_ERR_UNSUPPORTED;
     if constexpr (GLPR > 0) {
         if (a.n_rows > 0) {
-            const int64_t warps = (a.n_rows + 127) / 128;
+            // 128 rows per warp amortise the row-pointer fetches on big graphs; dataset-sized graphs (10^4 .. 10^5 rows) get 32
+            // rows per warp so that the grid still covers the SMs (CiteULike-shaped, 22.5k rows: 22 -> 88 CTAs)
+            const int rows_per_warp = a.n_rows >= (int64_t)148 * 24 * 128 ? 128 : 32;
+            const int64_t warps = (a.n_rows + rows_per_warp - 1) / rows_per_warp;
             const unsigned gblocks = (unsigned)((warps * 32 + kThreads - 1) / kThreads);
             cr::prof_start(cr::PROF_SPMM_ROWS, a.stream);
             if (a.val)
                 spmm_rows_grouped_kernel<GLPR, GNV, true><<<gblocks, kThreads, 0, a.stream>>>(
-                    a.rowptr, a.col, a.val, a.n_rows, a.X4, a.ep, long_row);
+                    a.rowptr, a.col, a.val, a.n_rows, a.X4, a.ep, long_row, rows_per_warp);
             else
                 spmm_rows_grouped_kernel<GLPR, GNV, false><<<gblocks, kThreads, 0, a.stream>>>(
-                    a.rowptr, a.col, a.val, a.n_rows, a.X4, a.ep, long_row);
+                    a.rowptr, a.col, a.val, a.n_rows, a.X4, a.ep, long_row, rows_per_warp);
             CR_LAUNCH_CHECK("spmm_rows_grouped_kernel");
             cr::prof_stop(cr::PROF_SPMM_ROWS, a.stream);
         }
@@ -395,7 +403,8 @@ int cr_spmm_plan(const int64_t* rowptr, int64_t n_rows, int64_t nnz, int d, void
     if (n_rows > 0) {
         const unsigned blocks = (unsigned)((n_rows + 255) / 256);
         spmm_plan_kernel<<<blocks, 256, 0, st>>>(rowptr, n_rows, (PlanHeader*)base, (LongRow*)(base + L.off_long),
-                                                 (Chunk*)(base + L.off_chunks), (int)L.max_long, (int)L.max_chunks);
+                                                 (Chunk*)(base + L.off_chunks), (int)L.max_long, (int)L.max_chunks, long_row_of(nnz),
+                                                 chunk_of(nnz));
         CR_LAUNCH_CHECK("spmm_plan_kernel");
     }
     return CR_OK;
@@ -414,7 +423,7 @@ static int spmm_entry(const int64_t* rowptr, const int32_t* col, const float* va
     SpmmArgs a{rowptr, col, val, n_rows, (const float4*)X, d / 4,
                Epi{(float4*)Y, (const float4*)(acc_in ? acc_in : acc), (float4*)acc, acc_beta, acc_div, (float4* const*)peers,
                    peers ? n_peers : 0, peer_row_offset * (d / 4), bcast_acc},
-               nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream};
+               nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream, long_row_of(nnz)};
     if (plan) {
         const PlanLayout L = plan_layout(nnz, d);
         if (plan_bytes < L.total) return CR_ERR_WORKSPACE;

@@ -170,7 +170,11 @@ __global__ void __launch_bounds__(kThreads) adam_step_kernel(float4* __restrict_
                                                              float* __restrict__ p, const float* __restrict__ g,
                                                              float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                              float w1, float beta2, float w2, float step_size, float bc2_sqrt,
-                                                             float eps, float grad_scale) {
+                                                             float eps, float grad_scale, const float* __restrict__ dev_scalars) {
+    if (dev_scalars) {      // CUDA-graph replay: the step-dependent bias corrections come from device memory
+        step_size = __ldg(dev_scalars);
+        bc2_sqrt = __ldg(dev_scalars + 1);
+    }
     auto upd = [&](float& pp, float gg, float& mm, float& vv) {
         gg *= grad_scale;
         mm = mm + (gg - mm) * w1;
@@ -304,8 +308,15 @@ int cr_bpr_fwd_bwd_f32(const float* user_emb, const float* item_emb, int d, cons
     });
 }
 
+int cr_adam_scalars(double lr, double beta1, double beta2, int64_t step, float* host_out2) {
+    if (!host_out2 || step < 1) return CR_ERR_ARG;
+    host_out2[0] = (float)(lr / (1.0 - pow(beta1, (double)step)));
+    host_out2[1] = (float)sqrt(1.0 - pow(beta2, (double)step));
+    return CR_OK;
+}
+
 int cr_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
-                     double beta2, double eps, int64_t step, float grad_scale, void* stream) {
+                     double beta2, double eps, int64_t step, float grad_scale, const float* dev_scalars, void* stream) {
     int rc = cr::require_device();
     if (rc != CR_OK) return rc;
     if (n < 0 || step < 1) return CR_ERR_ARG;
@@ -321,7 +332,7 @@ int cr_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp
     adam_step_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>((float4*)param, (const float4*)grad, (float4*)exp_avg,
                                                                    (float4*)exp_avg_sq, n4, param, grad, exp_avg, exp_avg_sq, n,
                                                                    (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), step_size,
-                                                                   bc2_sqrt, (float)eps, grad_scale);
+                                                                   bc2_sqrt, (float)eps, grad_scale, dev_scalars);
     CR_LAUNCH_CHECK("adam_step_kernel");
     return CR_OK;
 }

@@ -355,17 +355,27 @@ def bpr_fwd_bwd(user_emb, item_emb, u_idx, i_idx, j_idx, reg: float, grad_user, 
     return loss
 
 
-def adam_step(param, grad, exp_avg, exp_avg_sq, step: int, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0):
-    """In-place torch.optim.Adam update of one fp32 tensor (state tensors updated in place as well)."""
+def adam_scalars(step: int, lr: float, betas=(0.9, 0.999)):
+    """(lr / (1 - beta1^t), sqrt(1 - beta2^t)) as the library computes them, for ``dev_scalars`` of adam_step."""
+    out = (ctypes.c_float * 2)()
+    _lib.check(_lib.load().cr_adam_scalars(float(lr), float(betas[0]), float(betas[1]), int(step), out), "cr_adam_scalars")
+    return float(out[0]), float(out[1])
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step: int, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0,
+              dev_scalars=None):
+    """In-place torch.optim.Adam update of one fp32 tensor (state tensors updated in place as well).  With ``dev_scalars``
+    (device fp32[2] holding ``adam_scalars(step, ...)``) the step-dependent factors are read on the device (graph replay)."""
     lib = _lib.load()
     for t, name in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
         _req(t, torch.float32, name)
         if t.numel() != param.numel():
             raise ValueError(f"{name} has {t.numel()} elements, param has {param.numel()}")
-    dev = _same_device(param, grad, exp_avg, exp_avg_sq)
+    dev_scalars = _req(dev_scalars, torch.float32, "dev_scalars", optional=True)
+    dev = _same_device(param, grad, exp_avg, exp_avg_sq, dev_scalars)
     with torch.cuda.device(dev):
         rc = lib.cr_adam_step_f32(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(lr), float(betas[0]),
-                                  float(betas[1]), float(eps), int(step), float(grad_scale), _stream(dev))
+                                  float(betas[1]), float(eps), int(step), float(grad_scale), _ptr(dev_scalars), _stream(dev))
     _lib.check(rc, "cr_adam_step_f32")
     return param
 

@@ -201,9 +201,14 @@ CR_API int cr_bpr_fwd_bwd_f32(const float *user_emb, const float *item_emb, int 
 
 /* torch.optim.Adam(lr, betas, eps) single-tensor update (model/LightGCN.py:16 + optimizer.step() :28), no weight
  * decay / amsgrad; `step` is the 1-based step count; the gradient is read as grad * grad_scale.
- *   m += (g - m)(1 - beta1);  v = v beta2 + (1 - beta2) g g;  p -= lr/(1 - beta1^t) * m / (sqrt(v)/sqrt(1 - beta2^t) + eps) */
+ *   m += (g - m)(1 - beta1);  v = v beta2 + (1 - beta2) g g;  p -= lr/(1 - beta1^t) * m / (sqrt(v)/sqrt(1 - beta2^t) + eps)
+ * dev_scalars (device float[2], nullable): when given, the two step-dependent factors lr/(1 - beta1^t) and sqrt(1 - beta2^t)
+ * are read from device memory instead of being computed from `step` — a captured CUDA graph of the training step is then
+ * replayed for every step with only those 8 bytes refreshed (cr_adam_scalars fills the host copy). */
 CR_API int cr_adam_step_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, double lr,
-                            double beta1, double beta2, double eps, int64_t step, float grad_scale, void *stream);
+                            double beta1, double beta2, double eps, int64_t step, float grad_scale, const float *dev_scalars,
+                            void *stream);
+CR_API int cr_adam_scalars(double lr, double beta1, double beta2, int64_t step, float *host_out2);
 
 /* ------------------------------------------------------------------------------------------------
  * K6 — pairwise (user, positive, negative) sampler.

@@ -40,9 +40,14 @@ def case(name, n_users, n_items, edges, bs, layers=3, d=64, iters=5):
     t_prop = timed(lambda: step._forward(), iters)
     t_grad = timed(lambda: step.gradients(u, i, j), iters)
     t_step = timed(lambda: step.step(u, i, j), iters)
+    cap = step.capture(bs)
+    def replay():
+        smp.batch(0, 0, bs, out=cap.idx)
+        cap()
+    t_graph = timed(replay, iters * 4)
     nbytes_adam = N * d * 4 * 7
     print(json.dumps(dict(case=name, nnz=G.nnz, N=N, bs=bs, sample_ms=round(t_sample, 4), forward_ms=round(t_prop, 3), grad_ms=round(t_grad, 3),
-                          step_ms=round(t_step, 3), adam_ms=round(t_step - t_grad, 3), adam_GBps=round(nbytes_adam / ((t_step - t_grad) * 1e-3) / 1e9, 1),
+                          step_ms=round(t_step, 3), graph_step_ms=round(t_graph, 3), adam_ms=round(t_step - t_grad, 3), adam_GBps=round(nbytes_adam / ((t_step - t_grad) * 1e-3) / 1e9, 1),
                           loss=step.loss.cpu().tolist(), exhausted=int(smp.n_exhausted.item()))), flush=True)
     # big-batch sampler throughput
     nb = min(smp.n_pairs, 1 << 24)
