@@ -129,6 +129,19 @@ def make_step_plans(n_steps, n_q, n_users, n_items, seed, device):
     return plans
 
 
+def host_threads():
+    """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1: the CPU arms override it explicitly)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def score_workload(args, n_q):
+    return (f"C5 full-catalog top-{K} scoring: {args.n_users} users x {args.n_items} items, d={D}, {n_q} users/step, "
+            f"~{MASK_PER_USER} train-masked + {GT_PER_USER} gt items/user, Recall/NDCG@{TOPN} on device")
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -231,9 +244,7 @@ def run_b200(args):
         out.update(metric="full-rank users/sec (top-20 over catalog)", value=round(value, 1), unit="users/s", n_gpus=world,
                    steps=Ksteps, warmup=W, ms_per_step=round(ms / Ksteps, 3), higher_is_better=True, scaling="weak",
                    vs_baseline=None, dtype="tf32 select + f32 rescore", data="synthetic",
-                   config={"workload": f"C5 full-catalog top-{K} scoring: {args.n_users} users x {args.n_items} items, d={D}, "
-                                       f"{n_q} users/step, ~{MASK_PER_USER} train-masked + {GT_PER_USER} gt items/user, "
-                                       f"Recall/NDCG@{TOPN} on device",
+                   config={"workload": score_workload(args, n_q),
                            "parallelism": (f"user-sharded x{world}, item table replicated, no candidate exchange" if by_users else
                                            f"item-sharded x{world} + NCCL candidate all-gather") if world > 1 else "single GPU",
                            "l2": "inputs larger than L2 (item shard %.0f MB); no flush" % ((ie - ib) * D * 4 / 2**20),
@@ -400,6 +411,7 @@ def run_train_step(args, device, G, E0u, E0i, pk, lib):
 def cpu_score_baseline(user_tab, item_tab, plan_d, n_sample):
     """The reference's CPU path (oracle restatement of _evaluate + ranking_evaluation) on a bounded sample."""
     from oracle import coldrec_oracle as O
+    torch.set_num_threads(host_threads())
     U, I = user_tab.cpu(), item_tab.cpu()
     uids = plan_d["user_ids"][:n_sample].cpu().numpy()
     rp = plan_d["mask_rowptr"][:n_sample + 1].cpu().numpy()
@@ -416,6 +428,7 @@ def cpu_score_baseline(user_tab, item_tab, plan_d, n_sample):
 
 def cpu_spmm_baseline(G, E0u, E0i, frac=0.05):
     """torch.sparse.mm (COO, int64 indices) on the host cores, on a contiguous row sample of the adjacency."""
+    torch.set_num_threads(host_threads())
     n_rows = int(G.n_rows * frac)
     lo, hi = 0, int(G.rowptr[n_rows])
     rows = torch.repeat_interleave(torch.arange(n_rows, device=G.rowptr.device), (G.rowptr[1:n_rows + 1] - G.rowptr[:n_rows]))
@@ -436,6 +449,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import coldrec_oracle as O
+    torch.set_num_threads(host_threads())
     n_q = args.cpu_sample_users
     g = torch.Generator().manual_seed(1)
     U = torch.randn(args.n_users, D, generator=g) * 0.125
@@ -457,8 +471,9 @@ def run_reference(args):
     print(json.dumps(dict(impl="reference", metric="full-rank users/sec (top-20 over catalog)", value=round(value, 2), unit="users/s",
                           n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=round(dt / args.steps * 1e3, 1),
                           higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                          config={"workload": f"C5 full-catalog top-{K} scoring: {args.n_users} users x {args.n_items} items, d={D}; "
-                                              f"CPU sample of {n_q} users/step", "K": K, "n_items": args.n_items},
+                          config={"workload": score_workload(args, args.users_per_step * world), "parallelism": "host cores (CPU reference path)",
+                                  "users_per_step": args.users_per_step * world, "n_items": args.n_items, "K": K,
+                                  "sampled_users_per_step": n_q},
                           cpu_baseline={"value": round(value, 2), "unit": "users/s", "cores": cores, "kind": "port", "sample": sample},
                           e2e={"value": round(value, 2), "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           gpu_launches=0, check={"ndcg@20": perf[1][3]})), flush=True)
