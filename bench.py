@@ -315,7 +315,7 @@ def run_lightgcn(args, device, rank, world, pk, pk_src, lib):
         exchange = "SpMM epilogue peer stores over NVLink (fused all-gather)"
         try:
             PG.enable_p2p(D)
-            run = lambda: PG.propagate_p2p(E0, LAYERS)
+            run = lambda: PG.propagate_p2p(E0, LAYERS, copy=False)      # a view of the peer-mapped result table, like the fresh tensors of N=1
             run()
         except Exception as ex:      # symmetric memory unavailable on this box: NCCL all-gather after each layer
             print(f"[bench] peer-store path failed on rank {rank}: {type(ex).__name__}: {ex}", file=sys.stderr, flush=True)

@@ -123,15 +123,24 @@ __device__ __forceinline__ void reduce_groups(float4 (&a)[NV]) {
 // gather table — the all-gather of the next layer's input fused into the SpMM epilogue as peer-memory stores.
 struct Epi {
     float4* Y4; const float4* acc_in4; float4* acc4; float beta, div;
-    float4* const* peers; int n_peers; int64_t peer_off4;   // peers[p][peer_off4 + idx] = y (or the acc result)
+    float4* const* peers; int n_peers;
+    // peers[p][peer_off4 + idx] = y (or the acc result) for idx < peer_split4, peers[p][peer_off_hi4 + idx] above: local rows
+    // [0, split) and [split, n) may land in two different row ranges of the destination (a rank owns one range of user rows
+    // and one of item rows: the last layer is scattered straight into the original node numbering)
+    int64_t peer_off4, peer_split4, peer_off_hi4;
     int peers_get_acc;
 };
+
+__device__ __forceinline__ int64_t peer_index(const Epi& ep, int64_t idx) {
+    return idx + (idx < ep.peer_split4 ? ep.peer_off4 : ep.peer_off_hi4);
+}
 
 // y -> Y and/or acc = (beta*acc_in + y) / div for one float4 of one row (acc_in may alias acc).
 __device__ __forceinline__ void store_epilogue(const Epi& ep, int64_t idx, float4 y) {
     if (ep.Y4) ep.Y4[idx] = y;
     if (ep.peers && !ep.peers_get_acc) {
-        for (int p = 0; p < ep.n_peers; ++p) ep.peers[p][ep.peer_off4 + idx] = y;
+        const int64_t di = peer_index(ep, idx);
+        for (int p = 0; p < ep.n_peers; ++p) ep.peers[p][di] = y;
     }
     if (ep.acc4) {
         float4 o = y;
@@ -150,7 +159,8 @@ __device__ __forceinline__ void store_epilogue(const Epi& ep, int64_t idx, float
         }
         ep.acc4[idx] = o;
         if (ep.peers && ep.peers_get_acc) {
-            for (int p = 0; p < ep.n_peers; ++p) ep.peers[p][ep.peer_off4 + idx] = o;
+            const int64_t di = peer_index(ep, idx);
+            for (int p = 0; p < ep.n_peers; ++p) ep.peers[p][di] = o;
         }
     }
 }
@@ -412,17 +422,18 @@ int cr_spmm_plan(const int64_t* rowptr, int64_t n_rows, int64_t nnz, int d, void
 
 static int spmm_entry(const int64_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, int64_t nnz, const float* X,
                       int d, float* Y, const float* acc_in, float* acc, float acc_beta, float acc_div, void* plan,
-                      size_t plan_bytes, float* const* peers, int n_peers, int64_t peer_row_offset, int bcast_acc, void* stream) {
+                      size_t plan_bytes, float* const* peers, int n_peers, int64_t peer_row_offset, int64_t peer_row_split,
+                      int64_t peer_row_offset_hi, int bcast_acc, void* stream) {
     if (!rowptr || (!col && nnz > 0) || !X || n_rows < 0 || nnz < 0 || (!Y && !acc && !peers) || acc_div == 0.f) return CR_ERR_ARG;
     if (d <= 0 || d % 4 != 0 || d > 512) return CR_ERR_UNSUPPORTED;
     if (!cr::aligned16(X) || !cr::aligned16(Y) || !cr::aligned16(acc) || !cr::aligned16(acc_in)) return CR_ERR_ALIGN;
     if (acc_in && !acc) return CR_ERR_ARG;
-    if (peers && (n_peers < 1 || peer_row_offset < 0)) return CR_ERR_ARG;
+    if (peers && (n_peers < 1 || peer_row_offset < 0 || peer_row_split < 0 || peer_row_split + peer_row_offset_hi < 0)) return CR_ERR_ARG;
     int rc = cr::require_device();
     if (rc != CR_OK) return rc;
     SpmmArgs a{rowptr, col, val, n_rows, (const float4*)X, d / 4,
                Epi{(float4*)Y, (const float4*)(acc_in ? acc_in : acc), (float4*)acc, acc_beta, acc_div, (float4* const*)peers,
-                   peers ? n_peers : 0, peer_row_offset * (d / 4), bcast_acc},
+                   peers ? n_peers : 0, peer_row_offset * (d / 4), peer_row_split * (d / 4), peer_row_offset_hi * (d / 4), bcast_acc},
                nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream, long_row_of(nnz)};
     if (plan) {
         const PlanLayout L = plan_layout(nnz, d);
@@ -448,16 +459,16 @@ static int spmm_entry(const int64_t* rowptr, const int32_t* col, const float* va
 int cr_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, int64_t nnz,
                     const float* X, int d, float* Y, const float* acc_in, float* acc, float acc_beta, float acc_div,
                     void* plan, size_t plan_bytes, void* stream) {
-    return spmm_entry(rowptr, col, val, n_rows, nnz, X, d, Y, acc_in, acc, acc_beta, acc_div, plan, plan_bytes, nullptr, 0, 0, 0, stream);
+    return spmm_entry(rowptr, col, val, n_rows, nnz, X, d, Y, acc_in, acc, acc_beta, acc_div, plan, plan_bytes, nullptr, 0, 0, 0, 0, 0, stream);
 }
 
 int cr_spmm_csr_bcast_f32(const int64_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, int64_t nnz,
                           const float* X, int d, float* const* peer_tables, int n_peers, int64_t peer_row_offset,
-                          int bcast_acc, const float* acc_in, float* acc, float acc_beta, float acc_div, void* plan,
+                          int64_t peer_row_split, int64_t peer_row_offset_hi, int bcast_acc, const float* acc_in, float* acc, float acc_beta, float acc_div, void* plan,
                           size_t plan_bytes, void* stream) {
     if (!peer_tables || (bcast_acc && !acc)) return CR_ERR_ARG;
     return spmm_entry(rowptr, col, val, n_rows, nnz, X, d, nullptr, acc_in, acc, acc_beta, acc_div, plan, plan_bytes, peer_tables,
-                      n_peers, peer_row_offset, bcast_acc, stream);
+                      n_peers, peer_row_offset, peer_row_split, peer_row_offset_hi, bcast_acc, stream);
 }
 
 }  // extern "C"

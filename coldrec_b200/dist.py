@@ -148,11 +148,15 @@ class RowPartitionedGraph:
         sizes = [sum(e - b for b, e in pr) for pr in parts]
         self.rows_pad = int(max(sizes)) if self.n else 0
         self.padded_of = np.empty(self.n, dtype=np.int64)
+        self._ranges = []           # (global begin, global end, padded begin): the numbering is piecewise affine
         for r, pr in enumerate(parts):
             off = r * self.rows_pad
             for b, e in pr:
                 self.padded_of[b:e] = off + np.arange(e - b)
+                if e > b:
+                    self._ranges.append((int(b), int(e), int(off)))
                 off += e - b
+        self.n_local = int(sizes[self.rank])
         # local CSR: this rank's row ranges back to back, then empty padding rows
         mine = parts[self.rank]
         lens = np.concatenate([np.diff(rowptr[b:e + 1]) for b, e in mine]) if mine else np.zeros(0, dtype=np.int64)
@@ -172,13 +176,19 @@ class RowPartitionedGraph:
         self._spmm = spmm or (lambda g, X, **kw: g.spmm(X, **kw))
         self._padded_idx = t(self.padded_of)
 
-    def to_padded(self, E: torch.Tensor) -> torch.Tensor:
-        out = torch.zeros((self.world * self.rows_pad, E.shape[1]), dtype=E.dtype, device=E.device)
-        out[self._padded_idx] = E
+    def to_padded(self, E: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(N, d) in the reference's node numbering -> (W * rows_pad, d) padded numbering: 2 W contiguous block copies."""
+        if out is None:
+            out = torch.zeros((self.world * self.rows_pad, E.shape[1]), dtype=E.dtype, device=E.device)
+        for b, e, pb in self._ranges:
+            out[pb:pb + (e - b)].copy_(E[b:e])
         return out
 
     def from_padded(self, Ep: torch.Tensor) -> torch.Tensor:
-        return Ep[self._padded_idx]
+        out = torch.empty((self.n, Ep.shape[1]), dtype=Ep.dtype, device=Ep.device)
+        for b, e, pb in self._ranges:
+            out[b:e].copy_(Ep[pb:pb + (e - b)])
+        return out
 
     def propagate(self, E0: torch.Tensor, n_layers: int, include_ego: bool = True) -> torch.Tensor:
         """LightGCN-family propagation (model/LightGCN.py:86-96) over the row partition.  E0 is the full
@@ -211,30 +221,45 @@ class RowPartitionedGraph:
             self._xhdl.append(symm_mem.rendezvous(t, group=group))
             self._xbuf.append(t)
 
-    def propagate_p2p(self, E0: torch.Tensor, n_layers: int, include_ego: bool = True, padded_io: bool = False) -> torch.Tensor:
+    def propagate_p2p(self, E0: torch.Tensor, n_layers: int, include_ego: bool = True, padded_io: bool = False,
+                      copy: bool = True) -> torch.Tensor:
         """Same result as ``propagate``, but every finished row is stored by the SpMM epilogue straight into the
         gather table of all GPUs (``cr_spmm_csr_bcast_f32``): the per-layer all-gather overlaps the SpMM instead of
-        following it, and the final layer mean is broadcast the same way.  With ``padded_io`` E0 and the result are
-        in the padded node numbering (``to_padded`` / ``from_padded``), which an integrated pipeline keeps resident."""
+        following it.  The last layer's epilogue scatters the finished layer mean into every GPU's result table *in the
+        reference's node numbering* (two destination ranges per rank: its user rows and its item rows), so no
+        re-ordering pass follows.  With ``padded_io`` E0 and the result are in the padded numbering instead.  With
+        ``copy=False`` the result is a view of the peer-mapped result table, valid until the next call."""
         if getattr(self, "_p2p_d", None) != E0.shape[1]:
             self.enable_p2p(E0.shape[1])
-        W, r0 = self.world, self.rank * self.rows_pad
+        W, r0, nl = self.world, self.rank * self.rows_pad, self.n_local
         src, hdl = self._xbuf, self._xhdl
+        hdl[2].barrier()                     # nobody still reads the buffers of a previous call
         if padded_io:
             src[0].copy_(E0)
         else:
-            src[0][self._padded_idx] = E0      # padding rows are never referenced by a column id: no need to clear them
-        hdl[0].barrier()                     # nobody still reads the buffers of a previous call
+            self.to_padded(E0, out=src[0])   # padding rows are never referenced by a column id: no need to clear them
         count = n_layers + (1 if include_ego else 0)
         acc = torch.empty((self.rows_pad, E0.shape[1]), dtype=E0.dtype, device=E0.device)
         plan = self.local.plan(E0.shape[1])
+        rowptr = self.local.rowptr[:nl + 1]  # the padding rows are empty and nobody gathers them: not computed, not sent
+        mine = [(b, e) for b, e in self.parts[self.rank]]
+        scatter = (not padded_io) and len(mine) <= 2
         for k in range(1, n_layers + 1):
             last, first = k == n_layers, k == 1
             x = src[(k - 1) % 2]
             out_h = hdl[2] if last else hdl[k % 2]
-            ops.spmm_bcast(self.local.rowptr, self.local.col, self.local.val, x, out_h.buffer_ptrs_dev, W, r0, acc=acc,
+            off, split, off_hi = r0, None, 0
+            if last and scatter:             # local rows [0, n0) are global rows [b0, e0); the rest are [b1, e1)
+                n0 = mine[0][1] - mine[0][0]
+                off, split = mine[0][0], n0
+                off_hi = (mine[1][0] - n0) if len(mine) == 2 else 0
+            ops.spmm_bcast(rowptr, self.local.col, self.local.val, x, out_h.buffer_ptrs_dev, W, off, acc=acc,
                            acc_in=(x[r0:r0 + self.rows_pad] if (first and include_ego) else None),
                            acc_beta=(0.0 if (first and not include_ego) else 1.0), acc_div=(float(count) if last else 1.0),
-                           plan=plan, bcast_acc=last)
+                           plan=plan, bcast_acc=last, peer_row_split=split, peer_row_offset_hi=off_hi)
             out_h.barrier()                  # every GPU's rows have landed everywhere
-        return src[2] if padded_io else self.from_padded(src[2])
+        if padded_io:
+            res = src[2]
+        else:
+            res = src[2][:self.n] if scatter else self.from_padded(src[2])
+        return res.clone() if (copy and res.data_ptr() == src[2].data_ptr()) else res

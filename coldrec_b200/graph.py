@@ -66,6 +66,9 @@ class CsrGraph:
         return self._plans[d]
 
     def spmm(self, X, Y=None, acc=None, acc_in=None, acc_beta=1.0, acc_div=1.0):
+        """``torch.sparse.mm(adj, X)`` (model/LightGCN.py:90): a new (n_rows, d) tensor unless Y / acc are given."""
+        if Y is None and acc is None:
+            Y = torch.empty((self.n_rows, X.shape[1]), dtype=torch.float32, device=X.device)
         return ops.spmm(self.rowptr, self.col, self.val, X, Y=Y, acc=acc, acc_in=acc_in, acc_beta=acc_beta, acc_div=acc_div,
                         plan=self.plan(X.shape[1]))
 

@@ -63,7 +63,10 @@ def _worker(rank, world, port, ret):
         out_nccl = G.propagate(E0, 3).cpu().numpy()
         out_p2p = G.propagate_p2p(E0, 3).cpu().numpy()
         out_p2p_b = G.propagate_p2p(E0, 2, include_ego=False).cpu().numpy()     # buffers reused across calls
-        ret[rank] = dict(s=s.cpu().numpy(), i=i.cpu().numpy(), lo=lo, hi=hi, perf=perf, nccl=out_nccl, p2p=out_p2p, p2p_b=out_p2p_b)
+        out_p2p_c = G.from_padded(G.propagate_p2p(G.to_padded(E0), 3, padded_io=True)).cpu().numpy()   # padded numbering in and out
+        out_p2p_d = G.propagate_p2p(E0, 1, copy=False).cpu().numpy()            # single layer: first == last; view of the result table
+        ret[rank] = dict(s=s.cpu().numpy(), i=i.cpu().numpy(), lo=lo, hi=hi, perf=perf, nccl=out_nccl, p2p=out_p2p, p2p_b=out_p2p_b,
+                         p2p_c=out_p2p_c, p2p_d=out_p2p_d)
     finally:
         dist.destroy_process_group()
 
@@ -92,8 +95,9 @@ def test_two_gpu_sharded_scoring_and_fused_allgather_propagation():
     Ut, It = torch.from_numpy(c["U"]), torch.from_numpy(c["I"])
     ref = torch.cat(O.propagate(adj, Ut, It, 3)).numpy()
     ref_b = torch.cat(O.propagate(adj, Ut, It, 2, include_ego=False)).numpy()
+    ref_d = torch.cat(O.propagate(adj, Ut, It, 1)).numpy()
     for r in range(world):
-        for k, want_k in (("nccl", ref), ("p2p", ref), ("p2p_b", ref_b)):
+        for k, want_k in (("nccl", ref), ("p2p", ref), ("p2p_b", ref_b), ("p2p_c", ref), ("p2p_d", ref_d)):
             err = np.abs(ret[r][k] - want_k).max()
             assert err <= 1e-5 * np.abs(want_k).max(), f"rank {r} {k}: {err}"
     assert np.array_equal(ret[0]["p2p"], ret[1]["p2p"])
