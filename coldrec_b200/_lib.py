@@ -9,7 +9,8 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libcoldrec_b200.so")
+# CR_LIB_PATH: a differently built libcoldrec_b200.so (tools/build_variant.sh, kernel A/B runs); never a fallback
+LIB_PATH = os.environ.get("CR_LIB_PATH") or os.path.join(_HERE, "csrc", "libcoldrec_b200.so")
 
 CR_OK = 0
 CR_MAX_K = 64
@@ -31,7 +32,7 @@ SIGNATURES = {
     "cr_spmm_plan_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "cr_spmm_plan": (c_int, [_P, c_int64, c_int64, c_int, _P, c_size_t, _P]),
     "cr_spmm_csr_f32": (c_int, [_P, _P, _P, c_int64, c_int64, _P, c_int, _P, _P, _P, c_float, c_float, _P, c_size_t, _P]),
-    "cr_spmm_csr_bcast_f32": (c_int, [_P, _P, _P, c_int64, c_int64, _P, c_int, _P, c_int, c_int64, c_int64, c_int64, c_int, _P, _P, c_float,
+    "cr_spmm_csr_bcast_f32": (c_int, [_P, _P, _P, c_int64, c_int64, _P, c_int, _P, c_int, c_int64, c_int64, c_int64, c_int, _P, _P, _P, c_float,
                                       c_float, _P, c_size_t, _P]),
     "cr_score_topk_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int]),
     "cr_score_topk_f32": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int64, c_int, _P, _P, _P, c_uint8, c_int, _P, _P, _P,

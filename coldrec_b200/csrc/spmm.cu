@@ -20,6 +20,22 @@ constexpr int kSmallNnz = 1 << 23;  // dataset-sized graphs (MovieLens / CiteULi
 constexpr int kSmallLongRow = 64;   // bound: a 500-nonzero row walked by one 8-lane group is the whole kernel's critical path
 constexpr int kSmallChunk = 64;     // there, so they split at 64 nonzeros and spread the chunks over the idle SMs
 constexpr int kThreads = 256;
+// d = 64 geometry of the grouped kernel (A/B knobs, tools/build_variant.sh): lanes per row, gathers in flight per lane group,
+// CTAs per SM.  Measured on one box at C4 (3-layer propagation, ms): 8 lanes x 2 float4, U=4, 3 CTAs (80 regs) 31.6;
+// same with 4 CTAs (64 regs) 32.6; U=8 with 2 CTAs 33.0; 16 lanes x 1 float4: U=4 / 5 CTAs (48 regs) 41.9, U=8 / 5 CTAs 42.5,
+// U=8 / 3 CTAs 30.3, U=16 / 2 CTAs 34.9, **U=8 / 4 CTAs (64 regs) 29.4**; 4 lanes x 4 float4: 36.4 - 40.8.
+#ifndef CR_SPMM_GLPR
+#define CR_SPMM_GLPR 16
+#endif
+#ifndef CR_SPMM_U
+#define CR_SPMM_U 8
+#endif
+#ifndef CR_SPMM_MINB
+#define CR_SPMM_MINB 4
+#endif
+#ifndef CR_SPMM_LONG_U
+#define CR_SPMM_LONG_U 4      // gathers in flight per lane group in the warp-per-row / long-row-chunk kernels
+#endif
 inline int long_row_of(int64_t nnz) { return nnz >= kSmallNnz ? kLongRow : kSmallLongRow; }
 inline int chunk_of(int64_t nnz) { return nnz >= kSmallNnz ? kChunk : kSmallChunk; }
 
@@ -70,7 +86,7 @@ __device__ __forceinline__ void accumulate_range(const int32_t* __restrict__ col
                                                  int64_t s, int64_t e, const float4* __restrict__ X4, int d4, int lane,
                                                  float4 (&a)[NV]) {
     constexpr int G = 32 / LPR;
-    constexpr int U = 4;
+    constexpr int U = CR_SPMM_LONG_U;
     const int grp = lane / LPR, sub = lane % LPR;
     for (int64_t base = s; base < e; base += 32) {
         const int64_t j = base + lane;
@@ -129,6 +145,10 @@ struct Epi {
     // and one of item rows: the last layer is scattered straight into the original node numbering)
     int64_t peer_off4, peer_split4, peer_off_hi4;
     int peers_get_acc;
+    // optional: bit p of peer_need[row] says whether GPU p gathers this row at all (its row block has a nonzero in that
+    // column).  Most item rows of a bipartite graph have a handful of nonzeros, i.e. a handful of readers: the fused
+    // all-gather becomes a sparse one (C4, 8 GPUs: 2.9 remote copies per row instead of 7).
+    const uint8_t* peer_need;
 };
 
 __device__ __forceinline__ int64_t peer_index(const Epi& ep, int64_t idx) {
@@ -136,11 +156,14 @@ __device__ __forceinline__ int64_t peer_index(const Epi& ep, int64_t idx) {
 }
 
 // y -> Y and/or acc = (beta*acc_in + y) / div for one float4 of one row (acc_in may alias acc).
-__device__ __forceinline__ void store_epilogue(const Epi& ep, int64_t idx, float4 y) {
+__device__ __forceinline__ void store_epilogue(const Epi& ep, int64_t row, int64_t idx, float4 y) {
     if (ep.Y4) ep.Y4[idx] = y;
+    unsigned need = 0xffffffffu;
+    if (ep.peers && ep.peer_need) need = __ldg(ep.peer_need + row);
     if (ep.peers && !ep.peers_get_acc) {
         const int64_t di = peer_index(ep, idx);
-        for (int p = 0; p < ep.n_peers; ++p) ep.peers[p][di] = y;
+        for (int p = 0; p < ep.n_peers; ++p)
+            if ((need >> p) & 1u) ep.peers[p][di] = y;
     }
     if (ep.acc4) {
         float4 o = y;
@@ -160,7 +183,8 @@ __device__ __forceinline__ void store_epilogue(const Epi& ep, int64_t idx, float
         ep.acc4[idx] = o;
         if (ep.peers && ep.peers_get_acc) {
             const int64_t di = peer_index(ep, idx);
-            for (int p = 0; p < ep.n_peers; ++p) ep.peers[p][di] = o;
+            for (int p = 0; p < ep.n_peers; ++p)
+                if ((need >> p) & 1u) ep.peers[p][di] = o;
         }
     }
 }
@@ -182,7 +206,7 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
     if (lane < LPR) {
 #pragma unroll
         for (int nv = 0; nv < NV; ++nv)
-            if (!BOUNDS || lane + nv * LPR < d4) store_epilogue(ep, row * d4 + lane + nv * LPR, a[nv]);
+            if (!BOUNDS || lane + nv * LPR < d4) store_epilogue(ep, row, row * d4 + lane + nv * LPR, a[nv]);
     }
 }
 
@@ -193,13 +217,13 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
 // owns 128 consecutive rows: row pointers are fetched 32 rows at a time, column ids / values of the next batch
 // of rows and of the next chunk of the same row are prefetched while the current gathers are in flight, and
 // 32/LPR rows are gathered concurrently, so the chain is paid once per 32 rows instead of once per row.
-template <int LPR, int NV, bool HAS_VAL>
-__global__ void __launch_bounds__(kThreads, 3)
+template <int LPR, int NV, bool HAS_VAL, int U, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 spmm_rows_grouped_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
                          int64_t n_rows, const float4* __restrict__ X4, const Epi ep, int long_row, int kRowsPerWarp) {
-    constexpr int RPW = 32 / LPR;     // rows in flight per warp
-    constexpr int U = 4;              // gathers issued back to back per group
+    constexpr int RPW = 32 / LPR;     // rows in flight per warp; U = gathers issued back to back per group
     constexpr int d4 = LPR * NV;
+    static_assert(LPR % U == 0, "a group's LPR column ids are consumed U at a time");
     const int lane = threadIdx.x & 31, grp = lane / LPR, sub = lane % LPR;
     const int64_t row0 = (((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5) * kRowsPerWarp;
     if (row0 >= n_rows) return;
@@ -265,7 +289,7 @@ spmm_rows_grouped_kernel(const int64_t* __restrict__ rowptr, const int32_t* __re
             }
             if (!skip && row < n_rows) {
 #pragma unroll
-                for (int nv = 0; nv < NV; ++nv) store_epilogue(ep, row * d4 + sub + nv * LPR, a[nv]);
+                for (int nv = 0; nv < NV; ++nv) store_epilogue(ep, row, row * d4 + sub + nv * LPR, a[nv]);
             }
         }
     }
@@ -328,7 +352,7 @@ spmm_long_reduce_kernel(const PlanHeader* __restrict__ hdr, const LongRow* __res
                 const float4 p = partial4[(int64_t)(lr.chunk_base + c) * d4 + i];
                 sum.x += p.x; sum.y += p.y; sum.z += p.z; sum.w += p.w;
             }
-            store_epilogue(ep, (int64_t)lr.row * d4 + i, sum);
+            store_epilogue(ep, lr.row, (int64_t)lr.row * d4 + i, sum);
         }
     }
 }
@@ -341,7 +365,7 @@ struct SpmmArgs {
     int long_row;
 };
 
-template <int LPR, int NV, bool BOUNDS, int GLPR = 0, int GNV = 0>
+template <int LPR, int NV, bool BOUNDS, int GLPR = 0, int GNV = 0, int GU = 4, int GMINB = 3>
 int launch_spmm(const SpmmArgs& a) {
     const int long_row = a.hdr ? a.long_row : 0x7fffffff;
     const int64_t blocks = (a.n_rows * 32 + kThreads - 1) / kThreads;
@@ -355,10 +379,10 @@ int launch_spmm(const SpmmArgs& a) {
             const unsigned gblocks = (unsigned)((warps * 32 + kThreads - 1) / kThreads);
             cr::prof_start(cr::PROF_SPMM_ROWS, a.stream);
             if (a.val)
-                spmm_rows_grouped_kernel<GLPR, GNV, true><<<gblocks, kThreads, 0, a.stream>>>(
+                spmm_rows_grouped_kernel<GLPR, GNV, true, GU, GMINB><<<gblocks, kThreads, 0, a.stream>>>(
                     a.rowptr, a.col, a.val, a.n_rows, a.X4, a.ep, long_row, rows_per_warp);
             else
-                spmm_rows_grouped_kernel<GLPR, GNV, false><<<gblocks, kThreads, 0, a.stream>>>(
+                spmm_rows_grouped_kernel<GLPR, GNV, false, GU, GMINB><<<gblocks, kThreads, 0, a.stream>>>(
                     a.rowptr, a.col, a.val, a.n_rows, a.X4, a.ep, long_row, rows_per_warp);
             CR_LAUNCH_CHECK("spmm_rows_grouped_kernel");
             cr::prof_stop(cr::PROF_SPMM_ROWS, a.stream);
@@ -423,17 +447,18 @@ int cr_spmm_plan(const int64_t* rowptr, int64_t n_rows, int64_t nnz, int d, void
 static int spmm_entry(const int64_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, int64_t nnz, const float* X,
                       int d, float* Y, const float* acc_in, float* acc, float acc_beta, float acc_div, void* plan,
                       size_t plan_bytes, float* const* peers, int n_peers, int64_t peer_row_offset, int64_t peer_row_split,
-                      int64_t peer_row_offset_hi, int bcast_acc, void* stream) {
+                      int64_t peer_row_offset_hi, int bcast_acc, const uint8_t* peer_need, void* stream) {
     if (!rowptr || (!col && nnz > 0) || !X || n_rows < 0 || nnz < 0 || (!Y && !acc && !peers) || acc_div == 0.f) return CR_ERR_ARG;
     if (d <= 0 || d % 4 != 0 || d > 512) return CR_ERR_UNSUPPORTED;
     if (!cr::aligned16(X) || !cr::aligned16(Y) || !cr::aligned16(acc) || !cr::aligned16(acc_in)) return CR_ERR_ALIGN;
     if (acc_in && !acc) return CR_ERR_ARG;
+    if (peer_need && n_peers > 8) return CR_ERR_UNSUPPORTED;
     if (peers && (n_peers < 1 || peer_row_offset < 0 || peer_row_split < 0 || peer_row_split + peer_row_offset_hi < 0)) return CR_ERR_ARG;
     int rc = cr::require_device();
     if (rc != CR_OK) return rc;
     SpmmArgs a{rowptr, col, val, n_rows, (const float4*)X, d / 4,
                Epi{(float4*)Y, (const float4*)(acc_in ? acc_in : acc), (float4*)acc, acc_beta, acc_div, (float4* const*)peers,
-                   peers ? n_peers : 0, peer_row_offset * (d / 4), peer_row_split * (d / 4), peer_row_offset_hi * (d / 4), bcast_acc},
+                   peers ? n_peers : 0, peer_row_offset * (d / 4), peer_row_split * (d / 4), peer_row_offset_hi * (d / 4), bcast_acc, peers ? peer_need : nullptr},
                nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream, long_row_of(nnz)};
     if (plan) {
         const PlanLayout L = plan_layout(nnz, d);
@@ -446,7 +471,7 @@ static int spmm_entry(const int64_t* rowptr, const int32_t* col, const float* va
     }
     switch (d) {
         case 32: return launch_spmm<8, 1, false, 8, 1>(a);
-        case 64: return launch_spmm<16, 1, false, 8, 2>(a);
+        case 64: return launch_spmm<16, 1, false, CR_SPMM_GLPR, 16 / CR_SPMM_GLPR, CR_SPMM_U, CR_SPMM_MINB>(a);
         case 128: return launch_spmm<32, 1, false, 16, 2>(a);
         case 256: return launch_spmm<32, 2, false>(a);
         default:
@@ -459,16 +484,17 @@ static int spmm_entry(const int64_t* rowptr, const int32_t* col, const float* va
 int cr_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, int64_t nnz,
                     const float* X, int d, float* Y, const float* acc_in, float* acc, float acc_beta, float acc_div,
                     void* plan, size_t plan_bytes, void* stream) {
-    return spmm_entry(rowptr, col, val, n_rows, nnz, X, d, Y, acc_in, acc, acc_beta, acc_div, plan, plan_bytes, nullptr, 0, 0, 0, 0, 0, stream);
+    return spmm_entry(rowptr, col, val, n_rows, nnz, X, d, Y, acc_in, acc, acc_beta, acc_div, plan, plan_bytes, nullptr, 0, 0, 0, 0, 0, nullptr, stream);
 }
 
 int cr_spmm_csr_bcast_f32(const int64_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, int64_t nnz,
                           const float* X, int d, float* const* peer_tables, int n_peers, int64_t peer_row_offset,
-                          int64_t peer_row_split, int64_t peer_row_offset_hi, int bcast_acc, const float* acc_in, float* acc, float acc_beta, float acc_div, void* plan,
+                          int64_t peer_row_split, int64_t peer_row_offset_hi, int bcast_acc, const uint8_t* peer_need,
+                          const float* acc_in, float* acc, float acc_beta, float acc_div, void* plan,
                           size_t plan_bytes, void* stream) {
     if (!peer_tables || (bcast_acc && !acc)) return CR_ERR_ARG;
     return spmm_entry(rowptr, col, val, n_rows, nnz, X, d, nullptr, acc_in, acc, acc_beta, acc_div, plan, plan_bytes, peer_tables,
-                      n_peers, peer_row_offset, peer_row_split, peer_row_offset_hi, bcast_acc, stream);
+                      n_peers, peer_row_offset, peer_row_split, peer_row_offset_hi, bcast_acc, peer_need, stream);
 }
 
 }  // extern "C"

@@ -165,6 +165,7 @@ class RowPartitionedGraph:
         local_rp[len(lens) + 1:] = local_rp[len(lens)]
         col = np.asarray(col)
         local_col = np.concatenate([col[int(rowptr[b]):int(rowptr[e])] for b, e in mine]).astype(np.int64)
+        local_col_global = local_col.astype(np.int32)
         local_col = self.padded_of[local_col].astype(np.int32)
         local_val = None
         if val is not None:
@@ -175,6 +176,24 @@ class RowPartitionedGraph:
                               self.world * self.rows_pad, row_begin=self.rank * self.rows_pad)
         self._spmm = spmm or (lambda g, X, **kw: g.spmm(X, **kw))
         self._padded_idx = t(self.padded_of)
+        # same block with column ids in the reference's node numbering: the first layer of the peer-store path gathers
+        # straight from the caller's (N, d) table instead of from a re-ordered copy of it
+        self._col_global = t(local_col_global)
+        # Sparse all-gather masks (fused peer-store path, W <= 8): bit p of need[r] = "rank p has a nonzero in column r", i.e.
+        # p gathers row r in the next layer.  Item rows of a bipartite graph mostly have a handful of nonzeros, hence a
+        # handful of readers; only user rows (~100 nonzeros) are read everywhere.
+        self._need = self._seg_of_local = None
+        if 1 < self.world <= 8 and self.n:
+            need = np.zeros(self.n, dtype=np.uint8)
+            for r, pr in enumerate(parts):
+                seen = np.zeros(self.n, dtype=bool)
+                for b, e in pr:
+                    seen[col[int(rowptr[b]):int(rowptr[e])]] = True
+                need |= seen.astype(np.uint8) << np.uint8(r)
+            rows_mine = np.concatenate([np.arange(b, e) for b, e in mine]) if mine else np.zeros(0, dtype=np.int64)
+            self._need = t(need[rows_mine] | np.uint8(1 << self.rank))
+            self._seg_of_local = np.concatenate([np.full(e - b, k, dtype=np.int64) for k, (b, e) in enumerate(mine)]) if mine else rows_mine
+            self.need_copies = float(np.unpackbits(need[:, None], axis=1).sum() / max(self.n, 1))   # mean readers per row
 
     def to_padded(self, E: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """(N, d) in the reference's node numbering -> (W * rows_pad, d) padded numbering: 2 W contiguous block copies."""
@@ -222,41 +241,63 @@ class RowPartitionedGraph:
             self._xbuf.append(t)
 
     def propagate_p2p(self, E0: torch.Tensor, n_layers: int, include_ego: bool = True, padded_io: bool = False,
-                      copy: bool = True) -> torch.Tensor:
+                      copy: bool = True, sparse: bool = True, replicate_result: Optional[Sequence[int]] = None) -> torch.Tensor:
         """Same result as ``propagate``, but every finished row is stored by the SpMM epilogue straight into the
-        gather table of all GPUs (``cr_spmm_csr_bcast_f32``): the per-layer all-gather overlaps the SpMM instead of
-        following it.  The last layer's epilogue scatters the finished layer mean into every GPU's result table *in the
+        gather table of the GPUs that read it (``cr_spmm_csr_bcast_f32``): the per-layer all-gather overlaps the SpMM
+        instead of following it, and with ``sparse`` it only moves a row to the GPUs whose row block has a nonzero in
+        that column.  The last layer's epilogue scatters the finished layer mean into every GPU's result table *in the
         reference's node numbering* (two destination ranges per rank: its user rows and its item rows), so no
-        re-ordering pass follows.  With ``padded_io`` E0 and the result are in the padded numbering instead.  With
-        ``copy=False`` the result is a view of the peer-mapped result table, valid until the next call."""
+        re-ordering pass follows.  ``replicate_result`` = indices of the row classes (``segments``) whose result rows
+        every GPU receives — default all of them; ``(0,)`` replicates the user rows only and leaves each item row
+        with its owner, which is what item-sharded scoring consumes (rows of other owners are then undefined).
+        With ``padded_io`` E0 and the result are in the padded numbering instead.  With ``copy=False`` the result is
+        a view of the peer-mapped result table, valid until the next call."""
         if getattr(self, "_p2p_d", None) != E0.shape[1]:
             self.enable_p2p(E0.shape[1])
         W, r0, nl = self.world, self.rank * self.rows_pad, self.n_local
         src, hdl = self._xbuf, self._xhdl
         hdl[2].barrier()                     # nobody still reads the buffers of a previous call
-        if padded_io:
-            src[0].copy_(E0)
-        else:
-            self.to_padded(E0, out=src[0])   # padding rows are never referenced by a column id: no need to clear them
         count = n_layers + (1 if include_ego else 0)
         acc = torch.empty((self.rows_pad, E0.shape[1]), dtype=E0.dtype, device=E0.device)
+        mine = [(b, e) for b, e in self.parts[self.rank]]
+        if padded_io:
+            src[0].copy_(E0)
+            x0, col0 = src[0], self.local.col
+            if include_ego:
+                acc[:nl].copy_(E0[r0:r0 + nl])
+        else:                                # layer 1 reads the caller's table in place (column ids in its numbering)
+            x0, col0 = E0.contiguous(), self._col_global
+            o = 0
+            for b, e in mine:
+                if include_ego:
+                    acc[o:o + (e - b)].copy_(E0[b:e])
+                o += e - b
         plan = self.local.plan(E0.shape[1])
         rowptr = self.local.rowptr[:nl + 1]  # the padding rows are empty and nobody gathers them: not computed, not sent
-        mine = [(b, e) for b, e in self.parts[self.rank]]
         scatter = (not padded_io) and len(mine) <= 2
+        need = self._need if sparse else None
+        need_last = None
+        if replicate_result is not None and self._need is not None:
+            key = tuple(sorted(replicate_result))
+            cache = self.__dict__.setdefault("_need_last", {})
+            if key not in cache:
+                m = np.full(nl, 1 << self.rank, dtype=np.uint8)
+                m[np.isin(self._seg_of_local, key)] = (1 << W) - 1
+                cache[key] = torch.from_numpy(m).to(E0.device)
+            need_last = cache[key]
         for k in range(1, n_layers + 1):
             last, first = k == n_layers, k == 1
-            x = src[(k - 1) % 2]
+            x = x0 if first else src[(k - 1) % 2]
             out_h = hdl[2] if last else hdl[k % 2]
             off, split, off_hi = r0, None, 0
             if last and scatter:             # local rows [0, n0) are global rows [b0, e0); the rest are [b1, e1)
                 n0 = mine[0][1] - mine[0][0]
                 off, split = mine[0][0], n0
                 off_hi = (mine[1][0] - n0) if len(mine) == 2 else 0
-            ops.spmm_bcast(rowptr, self.local.col, self.local.val, x, out_h.buffer_ptrs_dev, W, off, acc=acc,
-                           acc_in=(x[r0:r0 + self.rows_pad] if (first and include_ego) else None),
+            ops.spmm_bcast(rowptr, col0 if first else self.local.col, self.local.val, x, out_h.buffer_ptrs_dev, W, off, acc=acc,
                            acc_beta=(0.0 if (first and not include_ego) else 1.0), acc_div=(float(count) if last else 1.0),
-                           plan=plan, bcast_acc=last, peer_row_split=split, peer_row_offset_hi=off_hi)
+                           plan=plan, bcast_acc=last, peer_row_split=split, peer_row_offset_hi=off_hi,
+                           peer_need=(need_last if last else need))
             out_h.barrier()                  # every GPU's rows have landed everywhere
         if padded_io:
             res = src[2]

@@ -123,8 +123,10 @@ def _worker(rank, world, port, ret):
         for ego in (True, False):
             out[ego] = G.propagate(E0, 3, include_ego=ego).numpy()
         out["seg"] = G2.propagate(E0, 3).numpy()
+        local = dict(rowptr=G2.local.rowptr.numpy(), col=G2.local.col.numpy(), val=G2.local.val.numpy(), need=G2._need.numpy(),
+                     n_local=G2.n_local, padded_of=G2.padded_of)
         ret[rank] = dict(s=s.numpy(), i=i.numpy(), lo=lo, hi=hi, perf=perf, prop=out, bounds=G.bounds, parts=G2.parts,
-                         rows_pad=G2.rows_pad, us=us.numpy(), ui=ui.numpy(), uperf=uperf)
+                         rows_pad=G2.rows_pad, us=us.numpy(), ui=ui.numpy(), uperf=uperf, local=local)
     finally:
         dist.destroy_process_group()
 
@@ -171,6 +173,46 @@ def test_sharded_scoring_and_partitioned_propagation_world2():
         (ub, ue), (ib, ie) = ret[r]["parts"][r]
         assert 0 <= ub < ue <= c["n_users"] <= ib < ie <= c["n_users"] + c["n_items"]
     assert ret[0]["rows_pad"] <= 0.6 * (c["n_users"] + c["n_items"])
+    _check_sparse_allgather(ret, world, torch.cat([Ut, It]).numpy(), ref)
+
+
+def _check_sparse_allgather(ret, world, E0, ref):
+    """The fused peer-store path only sends a row to the ranks whose need bit is set (cr_spmm_csr_bcast_f32, peer_need).
+    Emulated here with the workers' own local CSRs and masks: every table row a rank did not receive is NaN, so a row that
+    is read without having been sent poisons the result."""
+    rows_pad, N = ret[0]["rows_pad"], E0.shape[0]
+    loc = [ret[r]["local"] for r in range(world)]
+    padded_of = loc[0]["padded_of"]
+    A = [sp.csr_matrix((l["val"], l["col"], l["rowptr"]), shape=(rows_pad, world * rows_pad)) for l in loc]
+    # the masks are exact: bit p of need[row] <=> rank p's block has a nonzero in that (padded) column, or p owns the row
+    for r in range(world):
+        for p_ in range(world):
+            cols = np.zeros(world * rows_pad, dtype=bool)
+            cols[loc[p_]["col"]] = True
+            want = cols[r * rows_pad:r * rows_pad + loc[r]["n_local"]] | (p_ == r)
+            assert np.array_equal(((loc[r]["need"] >> p_) & 1).astype(bool), want)
+    full = np.zeros((world * rows_pad, E0.shape[1]), dtype=np.float64)
+    full[padded_of] = E0
+    tables = [full.copy() for _ in range(world)]
+    acc = [full[r * rows_pad:(r + 1) * rows_pad].copy() for r in range(world)]
+    for _ in range(3):
+        new = [np.full_like(full, np.nan) for _ in range(world)]
+        for r in range(world):
+            with np.errstate(invalid="ignore"):
+                # scipy multiplies explicit nonzeros only, like the kernel: NaN rows outside the pattern are never touched
+                y = A[r] @ np.where(np.isnan(tables[r]), 0.0, tables[r])
+                poisoned = (abs(A[r]).astype(bool).astype(np.float64) @ np.isnan(tables[r]).any(1).astype(np.float64)) > 0
+            assert not poisoned.any(), "a row was gathered that had not been sent to this rank"
+            acc[r] += y
+            n_l = loc[r]["n_local"]
+            for p_ in range(world):
+                sel = np.nonzero((loc[r]["need"] >> p_) & 1)[0]
+                new[p_][r * rows_pad + sel] = y[:n_l][sel]
+        tables = new
+    got = np.concatenate([a / 4.0 for a in acc])[padded_of]
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    sent = sum(int(np.unpackbits(l["need"][:, None], axis=1).sum()) for l in loc)
+    assert sent < world * N, "the masks should save some copies on this graph"
 
 
 def test_partition_helpers():
