@@ -47,8 +47,11 @@ def parse():
     ap.add_argument("--graph-edges", type=int, default=GRAPH_EDGES)
     ap.add_argument("--cpu-sample-users", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--shard", default="items", choices=["items", "users"],
-                    help="N>1 scoring layout: item-sharded + candidate all-gather (north star, default) or user-sharded (no exchange)")
+    ap.add_argument("--shard", default="auto", choices=["auto", "items", "users"],
+                    help="N>1 scoring layout.  items: the catalogue split N ways + NCCL candidate all-gather (north star).  auto "
+                         "(default): the same, but item shards are kept at >= --min-shard-items items; beyond that the ranks form "
+                         "user groups (N=8: four 2.5M-item shards x two user groups).  users: item table replicated, no exchange")
+    ap.add_argument("--min-shard-items", type=int, default=2_500_000)
     ap.add_argument("--prop-result", default="full", choices=["full", "users"],
                     help="multi-GPU propagation result: the whole table on every GPU (as at N=1), or user rows replicated + item rows "
                          "with their owner (what item-sharded scoring consumes)")
@@ -170,7 +173,7 @@ def barrier(world, device):
 def run_b200(args):
     import coldrec_b200 as cr
     from coldrec_b200 import _lib, ops
-    from coldrec_b200.dist import ShardedFullRankScorer, UserShardedFullRankScorer, shard_range
+    from coldrec_b200.dist import GridShardedFullRankScorer, grid_item_shards, shard_range
     from coldrec_b200.scoring import EvalPlan, HostBatchEvaluator
 
     rank, local_rank, world = dist_env()
@@ -190,13 +193,13 @@ def run_b200(args):
         n_q = args.users_per_step * world
         g = torch.Generator(device=device).manual_seed(1)
         user_tab = torch.randn(args.n_users, D, device=device, generator=g) * 0.125
-        by_users = args.shard == "users" and world > 1
-        ib, ie = (0, args.n_items) if by_users else shard_range(args.n_items, rank, world)
-        gi = torch.Generator(device=device).manual_seed(1000 + (0 if by_users else rank))
+        S = {"items": world, "users": 1, "auto": grid_item_shards(world, args.n_items, args.min_shard_items)}[args.shard]
+        scorer = GridShardedFullRankScorer(K, S, ops.SCORE_TF32_CHECKED)
+        ib, ie = scorer.item_range(args.n_items)
+        gi = torch.Generator(device=device).manual_seed(1000 + scorer.ishard)    # replicas of a shard hold the same rows
         item_shard = torch.randn(ie - ib, D, device=device, generator=gi) * 0.125
         plans_d = make_step_plans(W + Ksteps, n_q, args.n_users, args.n_items, 6, device)
         plans = [EvalPlan.from_arrays(**p) for p in plans_d]
-        scorer = (UserShardedFullRankScorer if by_users else ShardedFullRankScorer)(K, ops.SCORE_TF32_CHECKED)
 
         def step(plan):
             s, i = scorer.topk(user_tab, item_shard, ib, plan)
@@ -222,7 +225,7 @@ def run_b200(args):
         lib.cr_profile_enable(0)
         value = n_q * Ksteps / (ms * 1e-3)
         sweep_ms = tot.value / max(cnt.value, 1)
-        n_q_rank = (lambda r: r[1] - r[0])(shard_range(n_q, rank, world)) if by_users else n_q
+        n_q_rank = (lambda r: r[1] - r[0])(scorer.group_slice(n_q))      # users this rank sweeps against its item shard
         flops = 2.0 * n_q_rank * (ie - ib) * D                  # algorithmic FLOPs of one sweep launch (this rank's shard)
         tf32_peak = pk["bf16_tflops_sustained"] / 2.0             # TF32 dense = half the bf16 rate; kernel runs inside a long step
         achieved = flops / (sweep_ms * 1e-3) / 1e12 if sweep_ms > 0 else 0.0
@@ -249,8 +252,11 @@ def run_b200(args):
                    steps=Ksteps, warmup=W, ms_per_step=round(ms / Ksteps, 3), higher_is_better=True, scaling="weak",
                    vs_baseline=None, dtype="tf32 select + f32 rescore", data="synthetic",
                    config={"workload": score_workload(args, n_q),
-                           "parallelism": (f"user-sharded x{world}, item table replicated, no candidate exchange" if by_users else
-                                           f"item-sharded x{world} + NCCL candidate all-gather") if world > 1 else "single GPU",
+                           "parallelism": ("single GPU" if world == 1 else
+                                           f"user-sharded x{world}, item table replicated, no candidate exchange" if S == 1 else
+                                           f"item-sharded x{S} ({(ie - ib)} items per shard)"
+                                           + (f" x {world // S} user groups" if S < world else "")
+                                           + " + NCCL candidate all-gather" + (" inside each group" if S < world else "")),
                            "l2": "inputs larger than L2 (item shard %.0f MB); no flush" % ((ie - ib) * D * 4 / 2**20),
                            "users_per_step": n_q, "n_items": args.n_items, "K": K},
                    e2e={"value": round(n_q * Ksteps / (e2e_ms * 1e-3), 1), "unit": "users/s", "h2d_bytes_per_step": hb.h2d_bytes,

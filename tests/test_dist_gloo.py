@@ -215,6 +215,90 @@ def _check_sparse_allgather(ret, world, E0, ref):
     assert sent < world * N, "the masks should save some copies on this graph"
 
 
+def _cpu_scoring_callables(K):
+    """Oracle-backed stand-ins for the three CUDA entry points of the sharded scorer (same order as the kernels)."""
+    def local_topk(user_tab, item_tab, item_begin, plan, item_flags):
+        n_loc = item_tab.shape[0]
+        s = (user_tab[plan.user_ids.long()] @ item_tab.T).numpy().copy()
+        prp, pcol = plan.mask_rowptr.numpy(), plan.mask_col.numpy()
+        for j in range(plan.n_q):
+            m = pcol[prp[j]:prp[j + 1]] - item_begin
+            s[j, m[(m >= 0) & (m < n_loc)]] = O.MASK_SENTINEL
+        ids = np.broadcast_to(np.arange(item_begin, item_begin + n_loc, dtype=np.int32), s.shape)
+        ts, ti = _sorted_topk(s, ids, K)
+        return torch.from_numpy(ts), torch.from_numpy(ti)
+
+    def merge(gs, gi):
+        W, n, k = gs.shape
+        ts, ti = _sorted_topk(gs.permute(1, 0, 2).reshape(n, W * k).numpy(), gi.permute(1, 0, 2).reshape(n, W * k).numpy(), k)
+        return torch.from_numpy(ts), torch.from_numpy(ti)
+
+    def metrics(ids, rp, col, Ns):
+        sums = np.zeros((len(Ns), 6))
+        for a, N in enumerate(Ns):
+            for j in range(ids.shape[0]):
+                g = set(col[rp[j]:rp[j + 1]].tolist())
+                row = ids[j, :N].tolist()
+                hits = len(g.intersection(row))
+                dcg = sum(1.0 / np.log2(k + 2) for k, it in enumerate(row) if it in g)
+                idcg = sum(1.0 / np.log2(k + 2) for k in range(min(len(g), N)))
+                sums[a] += [hits, len(g), hits / len(g) if g else 0, 1 if g else 0, dcg / idcg if idcg else 0, 1 if idcg else 0]
+        return torch.from_numpy(sums)
+    return dict(local_topk=local_topk, merge=merge, metrics=metrics)
+
+
+def _grid_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from coldrec_b200.dist import GridShardedFullRankScorer
+        from coldrec_b200.scoring import EvalPlan
+        c = _case()
+        Ut, It = torch.from_numpy(c["U"]), torch.from_numpy(c["I"])
+        plan = EvalPlan.from_arrays(torch.from_numpy(c["uids"]), torch.from_numpy(c["rowptr"]), torch.from_numpy(c["col"]),
+                                    torch.from_numpy(c["gt_rowptr"]), torch.from_numpy(c["gt_col"]))
+        out = {}
+        for S in (1, 2, 4):          # user-sharded, 2 item shards x 2 user groups, pure item-sharded
+            sc = GridShardedFullRankScorer(c["K"], S, **_cpu_scoring_callables(c["K"]))
+            b, e = sc.item_range(c["n_items"])
+            s, i = sc.topk(Ut, It[b:e], b, plan)
+            lo, hi = sc.user_slice(plan.n_q)
+            out[S] = dict(s=s.numpy(), i=i.numpy(), lo=lo, hi=hi, perf=sc.metrics(i, plan, [10, 20], rounded=False), items=(b, e))
+        ret[rank] = out
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_grid_sharded_scoring_world4():
+    """2 item shards x 2 user groups (and the two degenerate grids) on 4 ranks: every user is ranked exactly once, lists equal
+    the single sweep bit for bit, all-reduced metrics equal the global ones."""
+    from coldrec_b200.dist import grid_item_shards
+    world = 4
+    ret = mp.Manager().dict()
+    mp.spawn(_grid_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    c = _case()
+    K = c["K"]
+    Ut, It = torch.from_numpy(c["U"]), torch.from_numpy(c["I"])
+    s_full = (Ut[torch.from_numpy(c["uids"]).long()] @ It.T).numpy().copy()
+    for j in range(len(c["uids"])):
+        s_full[j, c["col"][c["rowptr"][j]:c["rowptr"][j + 1]]] = O.MASK_SENTINEL
+    ts, ti = _sorted_topk(s_full, np.broadcast_to(np.arange(c["n_items"], dtype=np.int32), s_full.shape), K)
+    want = O.metrics_from_topk(ti.astype(np.int64), c["gt_rowptr"], c["gt_col"].astype(np.int64), [10, 20])
+    for S in (1, 2, 4):
+        seen = np.zeros(len(c["uids"]), dtype=int)
+        for r in range(world):
+            o = ret[r][S]
+            assert np.array_equal(o["i"], ti[o["lo"]:o["hi"]]), f"S={S} rank {r}: ids differ from the single sweep"
+            assert np.allclose(o["s"], ts[o["lo"]:o["hi"]], atol=1e-6)
+            assert np.allclose(o["perf"], want, atol=1e-9)
+            seen[o["lo"]:o["hi"]] += 1
+            assert o["items"][1] - o["items"][0] == c["n_items"] // S
+        assert (seen == 1).all(), f"S={S}: the user slices must tile the eval users"
+    assert [grid_item_shards(w, 10_000_000, 2_500_000) for w in (1, 2, 4, 8)] == [1, 2, 4, 4]
+    assert grid_item_shards(8, 10_000_000, 1) == 8 and grid_item_shards(8, 100, 1000) == 1 and grid_item_shards(6, 900, 250) == 3
+
+
 def test_partition_helpers():
     from coldrec_b200.dist import partition_rows_by_nnz, shard_range
     assert [shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]

@@ -55,6 +55,13 @@ def _worker(rank, world, port, ret):
         s, i = sc.topk(t(c["U"]), t(c["I"][b:e].copy()), b, plan)
         perf = sc.metrics(i, plan, [10, 20], rounded=False)
         lo, hi = sc.user_slice(plan.n_q)
+        from coldrec_b200.dist import GridShardedFullRankScorer
+        grid = {}
+        for S in (1, 2):                # user-sharded / item-sharded through the grid layout
+            gsc = GridShardedFullRankScorer(20, S, ops.SCORE_TF32_CHECKED)
+            gb, ge = gsc.item_range(c["n_items"])
+            g_s, g_i = gsc.topk(t(c["U"]), t(c["I"][gb:ge].copy()), gb, plan)
+            grid[S] = (g_i.cpu().numpy(), gsc.user_slice(plan.n_q), gsc.metrics(g_i, plan, [10, 20], rounded=False))
         adj = O.normalize_graph_mat(O.bipartite_adjacency(c["eu"], c["ei"], c["n_users"], c["n_items"])).tocsr()
         adj.sort_indices()
         G = RowPartitionedGraph(adj.indptr.astype(np.int64), adj.indices.astype(np.int64), adj.data.astype(np.float32), dev,
@@ -71,7 +78,7 @@ def _worker(rank, world, port, ret):
         (ub, ue), (ib, ie) = G.parts[rank]
         ret[rank] = dict(s=s.cpu().numpy(), i=i.cpu().numpy(), lo=lo, hi=hi, perf=perf, nccl=out_nccl, p2p=out_p2p, p2p_b=out_p2p_b,
                          p2p_c=out_p2p_c, p2p_d=out_p2p_d, p2p_e=out_p2p_e, p2p_f=out_p2p_f, own_items=(ib, ie),
-                         need_copies=G.need_copies)
+                         need_copies=G.need_copies, grid=grid)
     finally:
         dist.destroy_process_group()
 
@@ -95,6 +102,10 @@ def test_two_gpu_sharded_scoring_and_fused_allgather_propagation():
         assert np.array_equal(ret[r]["i"], i1[lo:hi]), "2-GPU ids must equal the single-GPU sweep bit for bit"
         assert np.allclose(ret[r]["s"], s1[lo:hi], atol=1e-6)
     want = O.metrics_from_topk(i1.astype(np.int64), c["gt_rowptr"], c["gt_col"].astype(np.int64), [10, 20])
+    for r in range(world):
+        for S in (1, 2):
+            g_i, (glo, ghi), g_perf = ret[r]["grid"][S]
+            assert np.array_equal(g_i, i1[glo:ghi]) and np.allclose(g_perf, want, atol=1e-9), f"grid S={S} rank {r}"
     assert np.allclose(ret[0]["perf"], want, atol=1e-9) and np.allclose(ret[1]["perf"], want, atol=1e-9)
     adj = O.normalize_graph_mat(O.bipartite_adjacency(c["eu"], c["ei"], c["n_users"], c["n_items"]))
     Ut, It = torch.from_numpy(c["U"]), torch.from_numpy(c["I"])
