@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--prop-result", default="full", choices=["full", "users"],
                     help="multi-GPU propagation result: the whole table on every GPU (as at N=1), or user rows replicated + item rows "
                          "with their owner (what item-sharded scoring consumes)")
+    ap.add_argument("--multicast", action="store_true",
+                    help="multi-GPU propagation: rows wanted by every GPU leave as one NVLS multimem.st (measured slower; default unicast)")
     ap.add_argument("--dense-exchange", action="store_true", help="multi-GPU propagation: send every row to every GPU (no need masks)")
     ap.add_argument("--no-train", action="store_true", help="skip the LightGCN training-step line of the lightgcn workload")
     ap.add_argument("--train-batch", type=int, default=4096)
@@ -327,10 +329,12 @@ def run_lightgcn(args, device, rank, world, pk, pk_src, lib):
             PG.enable_p2p(D)
             rep = None if args.prop_result == "full" else (0,)
             # copy=False: a view of the peer-mapped result table, like the fresh tensors of N=1
-            run = lambda: PG.propagate_p2p(E0, LAYERS, copy=False, sparse=not args.dense_exchange, replicate_result=rep)
+            run = lambda: PG.propagate_p2p(E0, LAYERS, copy=False, sparse=not args.dense_exchange, replicate_result=rep,
+                                           multicast=args.multicast)
             run()
             exchange += (", dense" if args.dense_exchange else f", rows sent only to the GPUs that gather them ({PG.need_copies:.2f} of {world} "
-                         f"copies per row)") + f", result: {args.prop_result}"
+                         f"copies per row)") + f", result: {args.prop_result}" + (
+                             ", rows wanted everywhere via NVLS multimem.st" if (PG.has_multicast and args.multicast) else ", unicast only")
         except Exception as ex:      # symmetric memory unavailable on this box: NCCL all-gather after each layer
             print(f"[bench] peer-store path failed on rank {rank}: {type(ex).__name__}: {ex}", file=sys.stderr, flush=True)
             exchange = f"NCCL all-gather per layer (peer path unavailable: {type(ex).__name__}: {str(ex)[:80]})"

@@ -32,8 +32,8 @@ SIGNATURES = {
     "cr_spmm_plan_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "cr_spmm_plan": (c_int, [_P, c_int64, c_int64, c_int, _P, c_size_t, _P]),
     "cr_spmm_csr_f32": (c_int, [_P, _P, _P, c_int64, c_int64, _P, c_int, _P, _P, _P, c_float, c_float, _P, c_size_t, _P]),
-    "cr_spmm_csr_bcast_f32": (c_int, [_P, _P, _P, c_int64, c_int64, _P, c_int, _P, c_int, c_int64, c_int64, c_int64, c_int, _P, _P, _P, c_float,
-                                      c_float, _P, c_size_t, _P]),
+    "cr_spmm_csr_bcast_f32": (c_int, [_P, _P, _P, c_int64, c_int64, _P, c_int, _P, c_int, c_int64, c_int64, c_int64, c_int, _P, _P, _P, _P,
+                                      c_float, c_float, _P, c_size_t, _P]),
     "cr_score_topk_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int]),
     "cr_score_topk_f32": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int64, c_int, _P, _P, _P, c_uint8, c_int, _P, _P, _P,
                                   c_int, _P, c_size_t, _P]),

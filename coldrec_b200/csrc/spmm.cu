@@ -149,7 +149,24 @@ struct Epi {
     // column).  Most item rows of a bipartite graph have a handful of nonzeros, i.e. a handful of readers: the fused
     // all-gather becomes a sparse one (C4, 8 GPUs: 2.9 remote copies per row instead of 7).
     const uint8_t* peer_need;
+    // optional NVLS multicast alias of the destination table: ONE multimem.st replicated by the switch replaces the n_peers
+    // unicast stores of a row that every GPU wants (user rows in every layer, all rows of a fully replicated result)
+    float4* mc4; unsigned all_mask;
 };
+
+__device__ __forceinline__ void multimem_st4(float4* p, const float4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ void store_peers(const Epi& ep, unsigned need, int64_t di, const float4& v) {
+    if (ep.mc4 && (need & ep.all_mask) == ep.all_mask) {
+        multimem_st4(ep.mc4 + di, v);
+        return;
+    }
+    for (int p = 0; p < ep.n_peers; ++p)
+        if ((need >> p) & 1u) ep.peers[p][di] = v;
+}
 
 __device__ __forceinline__ int64_t peer_index(const Epi& ep, int64_t idx) {
     return idx + (idx < ep.peer_split4 ? ep.peer_off4 : ep.peer_off_hi4);
@@ -161,9 +178,7 @@ __device__ __forceinline__ void store_epilogue(const Epi& ep, int64_t row, int64
     unsigned need = 0xffffffffu;
     if (ep.peers && ep.peer_need) need = __ldg(ep.peer_need + row);
     if (ep.peers && !ep.peers_get_acc) {
-        const int64_t di = peer_index(ep, idx);
-        for (int p = 0; p < ep.n_peers; ++p)
-            if ((need >> p) & 1u) ep.peers[p][di] = y;
+        store_peers(ep, need, peer_index(ep, idx), y);
     }
     if (ep.acc4) {
         float4 o = y;
@@ -182,9 +197,7 @@ __device__ __forceinline__ void store_epilogue(const Epi& ep, int64_t row, int64
         }
         ep.acc4[idx] = o;
         if (ep.peers && ep.peers_get_acc) {
-            const int64_t di = peer_index(ep, idx);
-            for (int p = 0; p < ep.n_peers; ++p)
-                if ((need >> p) & 1u) ep.peers[p][di] = o;
+            store_peers(ep, need, peer_index(ep, idx), o);
         }
     }
 }
@@ -447,18 +460,20 @@ int cr_spmm_plan(const int64_t* rowptr, int64_t n_rows, int64_t nnz, int d, void
 static int spmm_entry(const int64_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, int64_t nnz, const float* X,
                       int d, float* Y, const float* acc_in, float* acc, float acc_beta, float acc_div, void* plan,
                       size_t plan_bytes, float* const* peers, int n_peers, int64_t peer_row_offset, int64_t peer_row_split,
-                      int64_t peer_row_offset_hi, int bcast_acc, const uint8_t* peer_need, void* stream) {
+                      int64_t peer_row_offset_hi, int bcast_acc, const uint8_t* peer_need, float* mc_table, void* stream) {
     if (!rowptr || (!col && nnz > 0) || !X || n_rows < 0 || nnz < 0 || (!Y && !acc && !peers) || acc_div == 0.f) return CR_ERR_ARG;
     if (d <= 0 || d % 4 != 0 || d > 512) return CR_ERR_UNSUPPORTED;
     if (!cr::aligned16(X) || !cr::aligned16(Y) || !cr::aligned16(acc) || !cr::aligned16(acc_in)) return CR_ERR_ALIGN;
     if (acc_in && !acc) return CR_ERR_ARG;
-    if (peer_need && n_peers > 8) return CR_ERR_UNSUPPORTED;
+    if ((peer_need && n_peers > 8) || (peers && n_peers > 32)) return CR_ERR_UNSUPPORTED;
+    if (!cr::aligned16(mc_table)) return CR_ERR_ALIGN;
     if (peers && (n_peers < 1 || peer_row_offset < 0 || peer_row_split < 0 || peer_row_split + peer_row_offset_hi < 0)) return CR_ERR_ARG;
     int rc = cr::require_device();
     if (rc != CR_OK) return rc;
     SpmmArgs a{rowptr, col, val, n_rows, (const float4*)X, d / 4,
                Epi{(float4*)Y, (const float4*)(acc_in ? acc_in : acc), (float4*)acc, acc_beta, acc_div, (float4* const*)peers,
-                   peers ? n_peers : 0, peer_row_offset * (d / 4), peer_row_split * (d / 4), peer_row_offset_hi * (d / 4), bcast_acc, peers ? peer_need : nullptr},
+                   peers ? n_peers : 0, peer_row_offset * (d / 4), peer_row_split * (d / 4), peer_row_offset_hi * (d / 4), bcast_acc, peers ? peer_need : nullptr,
+                   peers ? (float4*)mc_table : nullptr, (peers && n_peers < 32) ? (1u << n_peers) - 1u : 0xffffffffu},
                nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream, long_row_of(nnz)};
     if (plan) {
         const PlanLayout L = plan_layout(nnz, d);
@@ -484,17 +499,17 @@ static int spmm_entry(const int64_t* rowptr, const int32_t* col, const float* va
 int cr_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, int64_t nnz,
                     const float* X, int d, float* Y, const float* acc_in, float* acc, float acc_beta, float acc_div,
                     void* plan, size_t plan_bytes, void* stream) {
-    return spmm_entry(rowptr, col, val, n_rows, nnz, X, d, Y, acc_in, acc, acc_beta, acc_div, plan, plan_bytes, nullptr, 0, 0, 0, 0, 0, nullptr, stream);
+    return spmm_entry(rowptr, col, val, n_rows, nnz, X, d, Y, acc_in, acc, acc_beta, acc_div, plan, plan_bytes, nullptr, 0, 0, 0, 0, 0, nullptr, nullptr, stream);
 }
 
 int cr_spmm_csr_bcast_f32(const int64_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, int64_t nnz,
                           const float* X, int d, float* const* peer_tables, int n_peers, int64_t peer_row_offset,
                           int64_t peer_row_split, int64_t peer_row_offset_hi, int bcast_acc, const uint8_t* peer_need,
-                          const float* acc_in, float* acc, float acc_beta, float acc_div, void* plan,
+                          float* mc_table, const float* acc_in, float* acc, float acc_beta, float acc_div, void* plan,
                           size_t plan_bytes, void* stream) {
     if (!peer_tables || (bcast_acc && !acc)) return CR_ERR_ARG;
     return spmm_entry(rowptr, col, val, n_rows, nnz, X, d, nullptr, acc_in, acc, acc_beta, acc_div, plan, plan_bytes, peer_tables,
-                      n_peers, peer_row_offset, peer_row_split, peer_row_offset_hi, bcast_acc, peer_need, stream);
+                      n_peers, peer_row_offset, peer_row_split, peer_row_offset_hi, bcast_acc, peer_need, mc_table, stream);
 }
 
 }  // extern "C"

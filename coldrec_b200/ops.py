@@ -91,12 +91,14 @@ def spmm(rowptr, col, val, X, Y=None, acc=None, acc_beta: float = 1.0, acc_div: 
 
 def spmm_bcast(rowptr, col, val, X, peer_tables_dev: int, n_peers: int, peer_row_offset: int, acc=None, acc_in=None,
                acc_beta: float = 1.0, acc_div: float = 1.0, plan=None, bcast_acc: bool = False, peer_row_split: Optional[int] = None,
-               peer_row_offset_hi: int = 0, peer_need=None):
+               peer_row_offset_hi: int = 0, peer_need=None, multicast_ptr: int = 0):
     """SpMM on the local row block whose finished rows are stored straight into every peer's gather table
     (``peer_tables_dev`` = device address of an array of ``n_peers`` table pointers, e.g. symmetric-memory
     ``buffer_ptrs_dev``).  Local row r lands in destination row ``peer_row_offset + r`` (r < ``peer_row_split``) or
     ``peer_row_offset_hi + r``; by default there is one destination range.  ``peer_need`` (uint8 per local row, bit p =
-    GPU p wants the row) restricts the stores to the GPUs that read the row.  The caller barriers the GPUs afterwards."""
+    GPU p wants the row) restricts the stores to the GPUs that read the row; ``multicast_ptr`` (NVLS multicast address of the
+    same tables, 0 = none) lets rows wanted everywhere go out as one switch-replicated store.  The caller barriers the GPUs
+    afterwards."""
     lib = _lib.load()
     rowptr = _req(rowptr, torch.int64, "rowptr"); col = _req(col, torch.int32, "col")
     val = _req(val, torch.float32, "val", optional=True); X = _req(X, torch.float32, "X")
@@ -111,7 +113,7 @@ def spmm_bcast(rowptr, col, val, X, peer_tables_dev: int, n_peers: int, peer_row
     with torch.cuda.device(dev):
         rc = lib.cr_spmm_csr_bcast_f32(_ptr(rowptr), _ptr(col), _ptr(val), n_rows, nnz, _ptr(X), d, ctypes.c_void_p(peer_tables_dev),
                                        n_peers, peer_row_offset, n_rows if peer_row_split is None else peer_row_split,
-                                       peer_row_offset_hi, int(bool(bcast_acc)), _ptr(peer_need), _ptr(acc_in), _ptr(acc), float(acc_beta),
+                                       peer_row_offset_hi, int(bool(bcast_acc)), _ptr(peer_need), ctypes.c_void_p(multicast_ptr or None), _ptr(acc_in), _ptr(acc), float(acc_beta),
                                        float(acc_div), _ptr(plan), 0 if plan is None else plan.numel(), _stream(dev))
     _lib.check(rc, "cr_spmm_csr_bcast_f32")
     return acc

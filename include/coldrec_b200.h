@@ -92,13 +92,15 @@ CR_API int cr_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const floa
  * bipartite row partition owns one block of user rows and one of item rows: the last layer lands directly in the
  * reference's node numbering (users then items, model/LightGCN.py:87,94-95).  peer_need (nullable, n_peers <= 8):
  * one byte per local row, bit p set iff GPU p reads that row in the next layer (or wants it in the result) — rows are
- * only stored where they are needed (a sparse all-gather); NULL = every row to every GPU.  The caller synchronises the GPUs between layers
+ * only stored where they are needed (a sparse all-gather); NULL = every row to every GPU.  mc_table (nullable): NVLS
+ * multicast address of the same destination table (torch symmetric memory `multicast_ptr`); a row wanted by every GPU is
+ * then written with ONE multimem.st that the NVSwitch replicates, instead of n_peers unicast stores.  The caller synchronises the GPUs between layers
  * (symmetric-memory barrier).  acc as in cr_spmm_csr_f32 (local rows); with bcast_acc != 0 the peers receive
  * the acc result (the finished layer mean) instead of y. */
 CR_API int cr_spmm_csr_bcast_f32(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n_rows, int64_t nnz,
                                  const float *X, int d, float *const *peer_tables, int n_peers, int64_t peer_row_offset,
                                  int64_t peer_row_split, int64_t peer_row_offset_hi, int bcast_acc, const uint8_t *peer_need,
-                                 const float *acc_in,
+                                 float *mc_table, const float *acc_in,
                                  float *acc, float acc_beta, float acc_div, void *plan, size_t plan_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------

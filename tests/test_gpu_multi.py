@@ -73,11 +73,12 @@ def _worker(rank, world, port, ret):
         out_p2p_c = G.from_padded(G.propagate_p2p(G.to_padded(E0), 3, padded_io=True)).cpu().numpy()   # padded numbering in and out
         out_p2p_d = G.propagate_p2p(E0, 1, copy=False).cpu().numpy()            # single layer: first == last; view of the result table
         out_p2p_e = G.propagate_p2p(E0, 3, sparse=False).cpu().numpy()          # dense all-gather (every row to every GPU)
+        out_p2p_g = G.propagate_p2p(E0, 3, multicast=True).cpu().numpy()        # NVLS multimem.st where the node has it
         # item-sharded consumers: user rows replicated, item rows stay with their owner
         out_p2p_f = G.propagate_p2p(E0, 3, replicate_result=(0,)).cpu().numpy()
         (ub, ue), (ib, ie) = G.parts[rank]
         ret[rank] = dict(s=s.cpu().numpy(), i=i.cpu().numpy(), lo=lo, hi=hi, perf=perf, nccl=out_nccl, p2p=out_p2p, p2p_b=out_p2p_b,
-                         p2p_c=out_p2p_c, p2p_d=out_p2p_d, p2p_e=out_p2p_e, p2p_f=out_p2p_f, own_items=(ib, ie),
+                         p2p_c=out_p2p_c, p2p_d=out_p2p_d, p2p_e=out_p2p_e, p2p_f=out_p2p_f, p2p_g=out_p2p_g, own_items=(ib, ie), has_multicast=G.has_multicast,
                          need_copies=G.need_copies, grid=grid)
     finally:
         dist.destroy_process_group()
@@ -113,7 +114,7 @@ def test_two_gpu_sharded_scoring_and_fused_allgather_propagation():
     ref_b = torch.cat(O.propagate(adj, Ut, It, 2, include_ego=False)).numpy()
     ref_d = torch.cat(O.propagate(adj, Ut, It, 1)).numpy()
     for r in range(world):
-        for k, want_k in (("nccl", ref), ("p2p", ref), ("p2p_b", ref_b), ("p2p_c", ref), ("p2p_d", ref_d), ("p2p_e", ref)):
+        for k, want_k in (("nccl", ref), ("p2p", ref), ("p2p_b", ref_b), ("p2p_c", ref), ("p2p_d", ref_d), ("p2p_e", ref), ("p2p_g", ref)):
             err = np.abs(ret[r][k] - want_k).max()
             assert err <= 1e-5 * np.abs(want_k).max(), f"rank {r} {k}: {err}"
         ib, ie = ret[r]["own_items"]
@@ -122,3 +123,5 @@ def test_two_gpu_sharded_scoring_and_fused_allgather_propagation():
             assert err <= 1e-5 * np.abs(ref).max(), f"rank {r} replicate_result=(0,): rows [{lo_},{hi_}) {err}"
         assert ret[r]["need_copies"] < world
     assert np.array_equal(ret[0]["p2p"], ret[1]["p2p"]) and np.array_equal(ret[0]["p2p"], ret[0]["p2p_e"])
+    assert np.array_equal(ret[0]["p2p"], ret[0]["p2p_g"]), "multicast and unicast stores must deliver the same bits"
+    print("NVLS multicast available:", ret[0]["has_multicast"])
