@@ -223,6 +223,30 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
     }
 }
 
+// One warp per chunk of a long row (grid-stride over the plan's chunk list), partial sums to the plan buffer.  Out of line:
+// it must not take registers from the row loop of the kernel that hosts it.
+template <int LPR, int NV, bool HAS_VAL>
+__device__ __noinline__ void walk_chunks(const PlanHeader* __restrict__ hdr, const Chunk* __restrict__ chunks,
+                                         const int32_t* __restrict__ col, const float* __restrict__ val,
+                                         const float4* __restrict__ X4, float4* __restrict__ partial4, int chunk_ctas) {
+    constexpr int d4 = LPR * NV;
+    const int lane = threadIdx.x & 31;
+    const int n_chunks = hdr->n_chunks;
+    const int warps = (chunk_ctas * kThreads) >> 5;
+    for (int c = (blockIdx.x * kThreads + threadIdx.x) >> 5; c < n_chunks; c += warps) {
+        const Chunk ch = chunks[c];
+        float4 a[NV];
+#pragma unroll
+        for (int nv = 0; nv < NV; ++nv) a[nv] = make_float4(0.f, 0.f, 0.f, 0.f);
+        accumulate_range<LPR, NV, HAS_VAL, false>(col, val, ch.start, ch.start + ch.len, X4, d4, lane, a);
+        reduce_groups<LPR, NV>(a);
+        if (lane < LPR) {
+#pragma unroll
+            for (int nv = 0; nv < NV; ++nv) partial4[(int64_t)c * d4 + lane + nv * LPR] = a[nv];
+        }
+    }
+}
+
 // Grouped variant (d = 4*LPR*NV with LPR < 32): the 32/LPR lane groups of a warp walk DIFFERENT rows.
 // ncu (profiles/r01) showed the warp-per-row kernel latency bound, not bandwidth bound (DRAM 31 % busy, 20
 // resident warps, long-scoreboard stalls): 80 % of the rows of a bipartite item-side graph have <= 8 nonzeros,
@@ -233,12 +257,21 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
 template <int LPR, int NV, bool HAS_VAL, int U, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
 spmm_rows_grouped_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
-                         int64_t n_rows, const float4* __restrict__ X4, const Epi ep, int long_row, int kRowsPerWarp) {
+                         int64_t n_rows, const float4* __restrict__ X4, const Epi ep, int long_row, int kRowsPerWarp,
+                         const PlanHeader* __restrict__ hdr, const Chunk* __restrict__ chunks, float4* __restrict__ partial4,
+                         int chunk_ctas) {
     constexpr int RPW = 32 / LPR;     // rows in flight per warp; U = gathers issued back to back per group
     constexpr int d4 = LPR * NV;
     static_assert(LPR % U == 0, "a group's LPR column ids are consumed U at a time");
     const int lane = threadIdx.x & 31, grp = lane / LPR, sub = lane % LPR;
-    const int64_t row0 = (((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5) * kRowsPerWarp;
+    if ((int)blockIdx.x < chunk_ctas) {
+        // The first CTAs of the grid walk the chunks of the long rows (one warp per chunk, partial sums to the plan buffer):
+        // the longest work items start first and share the launch — and its tail — with the ordinary rows instead of
+        // following them in a kernel of their own.
+        walk_chunks<LPR, NV, HAS_VAL>(hdr, chunks, col, val, X4, partial4, chunk_ctas);
+        return;
+    }
+    const int64_t row0 = (((int64_t)(blockIdx.x - chunk_ctas) * kThreads + threadIdx.x) >> 5) * kRowsPerWarp;
     if (row0 >= n_rows) return;
     const int64_t row_end = min(n_rows, row0 + kRowsPerWarp);
     for (int64_t r32 = row0; r32 < row_end; r32 += 32) {
@@ -351,52 +384,84 @@ spmm_long_chunks_kernel(const PlanHeader* __restrict__ hdr, const Chunk* __restr
     }
 }
 
+// Partial sums of a long row -> the row, in a fixed order (deterministic, no atomics).  A warp per row; for d <= 64 the
+// 32/d4 lane groups take every G-th chunk each and every group keeps four independent running sums, so the head rows
+// (hundreds of chunks) cost ~n_chunks/(4G) dependent L2 round trips instead of n_chunks (0.37 ms per layer at C4 before).
 __global__ void __launch_bounds__(kThreads)
 spmm_long_reduce_kernel(const PlanHeader* __restrict__ hdr, const LongRow* __restrict__ long_rows,
                         const float4* __restrict__ partial4, int d4, const Epi ep) {
     const int lane = threadIdx.x & 31;
     const int n_long = hdr->n_long;
     const int warps = (gridDim.x * kThreads) >> 5;
+    const int G = d4 <= 16 ? 32 / d4 : 1;               // d4 in {8, 16} (d = 32, 64): 4 or 2 lane groups; otherwise one
+    const auto add = [](float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; };
     for (int li = (blockIdx.x * kThreads + threadIdx.x) >> 5; li < n_long; li += warps) {
         const LongRow lr = long_rows[li];
-        for (int i = lane; i < d4; i += 32) {
-            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int c = 0; c < lr.n_chunks; ++c) {     // fixed chunk order: deterministic
-                const float4 p = partial4[(int64_t)(lr.chunk_base + c) * d4 + i];
-                sum.x += p.x; sum.y += p.y; sum.z += p.z; sum.w += p.w;
+        if (G > 1 && 32 % d4 == 0) {
+            const int g = lane / d4, i = lane % d4;
+            const float4* base = partial4 + (int64_t)lr.chunk_base * d4 + i;
+            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+            int c = g;
+            for (; c + 3 * G < lr.n_chunks; c += 4 * G) {
+                const float4 p0 = base[(int64_t)c * d4], p1 = base[(int64_t)(c + G) * d4];
+                const float4 p2 = base[(int64_t)(c + 2 * G) * d4], p3 = base[(int64_t)(c + 3 * G) * d4];
+                add(s0, p0); add(s1, p1); add(s2, p2); add(s3, p3);
             }
-            store_epilogue(ep, lr.row, (int64_t)lr.row * d4 + i, sum);
+            for (; c < lr.n_chunks; c += G) add(s0, base[(int64_t)c * d4]);
+            add(s0, s1); add(s2, s3); add(s0, s2);
+            for (int off = d4; off < 32; off <<= 1) {
+                s0.x += __shfl_down_sync(CR_FULL_MASK, s0.x, off);
+                s0.y += __shfl_down_sync(CR_FULL_MASK, s0.y, off);
+                s0.z += __shfl_down_sync(CR_FULL_MASK, s0.z, off);
+                s0.w += __shfl_down_sync(CR_FULL_MASK, s0.w, off);
+            }
+            if (lane < d4) store_epilogue(ep, lr.row, (int64_t)lr.row * d4 + i, s0);
+        } else {
+            for (int i = lane; i < d4; i += 32) {
+                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int c = 0; c < lr.n_chunks; ++c) add(sum, partial4[(int64_t)(lr.chunk_base + c) * d4 + i]);
+                store_epilogue(ep, lr.row, (int64_t)lr.row * d4 + i, sum);
+            }
         }
     }
 }
 
 struct SpmmArgs {
-    const int64_t* rowptr; const int32_t* col; const float* val; int64_t n_rows; const float4* X4; int d4;
+    const int64_t* rowptr; const int32_t* col; const float* val; int64_t n_rows; int64_t nnz; const float4* X4; int d4;
     Epi ep;
     PlanHeader* hdr; LongRow* long_rows; Chunk* chunks; float4* partial4;
     cudaStream_t stream;
     int long_row;
 };
 
-template <int LPR, int NV, bool BOUNDS, int GLPR = 0, int GNV = 0, int GU = 4, int GMINB = 3>
+template <int LPR, int NV, bool BOUNDS, int GLPR = 0, int GNV = 0, int GU = 4, int GMINB = 3, int SLPR = GLPR, int SNV = GNV>
 int launch_spmm(const SpmmArgs& a) {
     const int long_row = a.hdr ? a.long_row : 0x7fffffff;
+    bool chunks_fused = false;
     const int64_t blocks = (a.n_rows * 32 + kThreads - 1) / kThreads;
     if (blocks > 0x7fffffffLL) return CR_ERR_UNSUPPORTED;
     if constexpr (GLPR > 0) {
         if (a.n_rows > 0) {
             // 128 rows per warp amortise the row-pointer fetches on big graphs; dataset-sized graphs (10^4 .. 10^5 rows) get 32
             // rows per warp so that the grid still covers the SMs (CiteULike-shaped, 22.5k rows: 22 -> 88 CTAs)
-            const int rows_per_warp = a.n_rows >= (int64_t)148 * 24 * 128 ? 128 : 32;
+            const bool big = a.n_rows >= (int64_t)148 * 24 * 128;
+            const int rows_per_warp = big ? 128 : 32;
             const int64_t warps = (a.n_rows + rows_per_warp - 1) / rows_per_warp;
-            const unsigned gblocks = (unsigned)((warps * 32 + kThreads - 1) / kThreads);
+            // long-row chunks ride in the first CTAs of the same launch (the plan lives on the device: size by its upper bound)
+            const int64_t max_chunks = a.hdr ? a.nnz / chunk_of(a.nnz) + a.nnz / (long_row_of(a.nnz) + 1) + 2 : 0;
+            const int chunk_ctas = (int)min((int64_t)148 * GMINB, (max_chunks * 32 + kThreads - 1) / kThreads);
+            chunks_fused = a.hdr != nullptr;
+            const unsigned gblocks = (unsigned)((warps * 32 + kThreads - 1) / kThreads) + (unsigned)chunk_ctas;
             cr::prof_start(cr::PROF_SPMM_ROWS, a.stream);
-            if (a.val)
-                spmm_rows_grouped_kernel<GLPR, GNV, true, GU, GMINB><<<gblocks, kThreads, 0, a.stream>>>(
-                    a.rowptr, a.col, a.val, a.n_rows, a.X4, a.ep, long_row, rows_per_warp);
-            else
-                spmm_rows_grouped_kernel<GLPR, GNV, false, GU, GMINB><<<gblocks, kThreads, 0, a.stream>>>(
-                    a.rowptr, a.col, a.val, a.n_rows, a.X4, a.ep, long_row, rows_per_warp);
+            // Bandwidth-bound graphs take the (GLPR, GU, GMINB) geometry; dataset-sized ones are latency bound and keep more rows
+            // in flight per warp with the narrower groups (SLPR lanes x SNV float4, 4 gathers, 3 CTAs/SM): CiteULike-shaped
+            // training step 0.37 ms vs 0.43 ms with the wide geometry.
+#define CR_GROUPED(L_, N_, V_, U_, B_)                                                                                          \
+    spmm_rows_grouped_kernel<L_, N_, V_, U_, B_><<<gblocks, kThreads, 0, a.stream>>>(                                           \
+        a.rowptr, a.col, a.val, a.n_rows, a.X4, a.ep, long_row, rows_per_warp, a.hdr, a.chunks, a.partial4, chunk_ctas)
+            if (big) { if (a.val) CR_GROUPED(GLPR, GNV, true, GU, GMINB); else CR_GROUPED(GLPR, GNV, false, GU, GMINB); }
+            else { if (a.val) CR_GROUPED(SLPR, SNV, true, 4, 3); else CR_GROUPED(SLPR, SNV, false, 4, 3); }
+#undef CR_GROUPED
             CR_LAUNCH_CHECK("spmm_rows_grouped_kernel");
             cr::prof_stop(cr::PROF_SPMM_ROWS, a.stream);
         }
@@ -413,13 +478,15 @@ int launch_spmm(const SpmmArgs& a) {
     }
     if (a.hdr) {
         const int grid = 148 * 8;
-        if (a.val)
-            spmm_long_chunks_kernel<LPR, NV, true, BOUNDS><<<grid, kThreads, 0, a.stream>>>(a.hdr, a.chunks, a.col, a.val,
-                                                                                            a.X4, a.d4, a.partial4);
-        else
-            spmm_long_chunks_kernel<LPR, NV, false, BOUNDS><<<grid, kThreads, 0, a.stream>>>(a.hdr, a.chunks, a.col, a.val,
-                                                                                             a.X4, a.d4, a.partial4);
-        CR_LAUNCH_CHECK("spmm_long_chunks_kernel");
+        if (!chunks_fused) {
+            if (a.val)
+                spmm_long_chunks_kernel<LPR, NV, true, BOUNDS><<<grid, kThreads, 0, a.stream>>>(a.hdr, a.chunks, a.col, a.val,
+                                                                                                a.X4, a.d4, a.partial4);
+            else
+                spmm_long_chunks_kernel<LPR, NV, false, BOUNDS><<<grid, kThreads, 0, a.stream>>>(a.hdr, a.chunks, a.col, a.val,
+                                                                                                 a.X4, a.d4, a.partial4);
+            CR_LAUNCH_CHECK("spmm_long_chunks_kernel");
+        }
         spmm_long_reduce_kernel<<<148, kThreads, 0, a.stream>>>(a.hdr, a.long_rows, a.partial4, a.d4, a.ep);
         CR_LAUNCH_CHECK("spmm_long_reduce_kernel");
     }
@@ -470,7 +537,7 @@ static int spmm_entry(const int64_t* rowptr, const int32_t* col, const float* va
     if (peers && (n_peers < 1 || peer_row_offset < 0 || peer_row_split < 0 || peer_row_split + peer_row_offset_hi < 0)) return CR_ERR_ARG;
     int rc = cr::require_device();
     if (rc != CR_OK) return rc;
-    SpmmArgs a{rowptr, col, val, n_rows, (const float4*)X, d / 4,
+    SpmmArgs a{rowptr, col, val, n_rows, nnz, (const float4*)X, d / 4,
                Epi{(float4*)Y, (const float4*)(acc_in ? acc_in : acc), (float4*)acc, acc_beta, acc_div, (float4* const*)peers,
                    peers ? n_peers : 0, peer_row_offset * (d / 4), peer_row_split * (d / 4), peer_row_offset_hi * (d / 4), bcast_acc, peers ? peer_need : nullptr,
                    peers ? (float4*)mc_table : nullptr, (peers && n_peers < 32) ? (1u << n_peers) - 1u : 0xffffffffu},
@@ -486,7 +553,7 @@ static int spmm_entry(const int64_t* rowptr, const int32_t* col, const float* va
     }
     switch (d) {
         case 32: return launch_spmm<8, 1, false, 8, 1>(a);
-        case 64: return launch_spmm<16, 1, false, CR_SPMM_GLPR, 16 / CR_SPMM_GLPR, CR_SPMM_U, CR_SPMM_MINB>(a);
+        case 64: return launch_spmm<16, 1, false, CR_SPMM_GLPR, 16 / CR_SPMM_GLPR, CR_SPMM_U, CR_SPMM_MINB, 8, 2>(a);
         case 128: return launch_spmm<32, 1, false, 16, 2>(a);
         case 256: return launch_spmm<32, 2, false>(a);
         default:
