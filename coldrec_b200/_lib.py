@@ -42,6 +42,7 @@ SIGNATURES = {
     "cr_topk_merge": (c_int, [_P, _P, c_int, c_int64, c_int, _P, _P, _P]),
     "cr_fill_masked": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, c_uint8, _P, _P, _P]),
     "cr_gather_rows_f32": (c_int, [_P, _P, c_int64, c_int, _P, _P]),
+    "cr_copy_rows_f32": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P]),
     "cr_rank_metrics_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "cr_rank_metrics": (c_int, [_P, c_int64, c_int, _P, _P, ctypes.POINTER(c_int32), c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "cr_linear_act_f32": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, _P, c_int64, _P, _P, _P, _P, c_int, c_int, _P,

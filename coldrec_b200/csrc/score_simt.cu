@@ -268,6 +268,17 @@ __global__ void gather_rows_kernel(const float4* __restrict__ src, const int32_t
     dst[i] = __ldg(src + (int64_t)__ldg(ids + r) * d4 + c);
 }
 
+// dst[dst_ids ? dst_ids[j] : j, :] = src[src_ids ? src_ids[j] : j, :]
+__global__ void copy_rows_kernel(const float4* __restrict__ src, const int32_t* __restrict__ src_ids,
+                                 const int32_t* __restrict__ dst_ids, int64_t n, int d4, float4* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * d4) return;
+    const int64_t r = i / d4;
+    const int c = (int)(i % d4);
+    const int64_t sr = src_ids ? (int64_t)__ldg(src_ids + r) : r, dr = dst_ids ? (int64_t)__ldg(dst_ids + r) : r;
+    dst[dr * d4 + c] = __ldg(src + sr * d4 + c);
+}
+
 // Queries that found fewer than K candidates in the swept (flag-compacted) tables: the reference would
 // list masked ids at CR_MASK_SCORE there (any of them: they tie), so fill with the smallest masked ids.
 __global__ void fill_masked_kernel(float* __restrict__ out_score, int32_t* __restrict__ out_id, int64_t n_q, int K,
@@ -429,6 +440,21 @@ int cr_gather_rows_f32(const float* src, const int32_t* ids, int64_t n, int d, f
     if (blocks > 0x7fffffffLL) return CR_ERR_UNSUPPORTED;
     gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)src, ids, n, d / 4, (float4*)dst);
     CR_LAUNCH_CHECK("gather_rows_kernel");
+    return CR_OK;
+}
+
+int cr_copy_rows_f32(const float* src, const int32_t* src_ids, const int32_t* dst_ids, int64_t n, int d, float* dst, void* stream) {
+    if (!src || !dst || n < 0) return CR_ERR_ARG;
+    if (d <= 0 || d % 4 != 0) return CR_ERR_UNSUPPORTED;
+    if (!cr::aligned16(src) || !cr::aligned16(dst)) return CR_ERR_ALIGN;
+    int rc = cr::require_device();
+    if (rc != CR_OK) return rc;
+    if (n == 0) return CR_OK;
+    const int64_t total = n * (d / 4);
+    const int64_t blocks = (total + 255) / 256;
+    if (blocks > 0x7fffffffLL) return CR_ERR_UNSUPPORTED;
+    copy_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)src, src_ids, dst_ids, n, d / 4, (float4*)dst);
+    CR_LAUNCH_CHECK("copy_rows_kernel");
     return CR_OK;
 }
 

@@ -156,6 +156,29 @@ def propagate(graph: CsrGraph, user_emb: torch.Tensor, item_emb: torch.Tensor, n
     return acc[:n_u], acc[n_u:]
 
 
+def propagate_frozen_cold(graph: CsrGraph, user_emb: torch.Tensor, item_x: torch.Tensor, n_layers: int,
+                          cold_item_idx: torch.Tensor) -> List[torch.Tensor]:
+    """CGRC ``_propagate_gprime_frozen_cold`` (model/CGRC.py:76-93): LightGCN convolutions on G' in which the cold item
+    rows are put back to their content vector ``item_x[cold]`` after every layer.  Returns the layer list
+    [h^(0), ..., h^(L)], each (n_users + n_items, d).  ``cold_item_idx``: dense item ids (any integer dtype, may be empty)."""
+    if n_layers < 1:
+        raise ValueError("n_layers must be >= 1")
+    n_u = user_emb.shape[0]
+    item_x = item_x.contiguous()
+    cold = cold_item_idx.to(device=item_x.device, dtype=torch.int32).contiguous()
+    cold_rows = (cold + n_u).contiguous()
+    h = torch.cat([user_emb, item_x], 0).contiguous()
+    if h.shape[0] != graph.n_cols or graph.n_rows != graph.n_cols:
+        raise ValueError(f"adjacency is {graph.n_rows}x{graph.n_cols}, embeddings have {h.shape[0]} rows")
+    out = [h]
+    for _ in range(n_layers):
+        h = graph.spmm(h)
+        if cold.numel():
+            ops.copy_rows(item_x, h, src_ids=cold, dst_ids=cold_rows)
+        out.append(h)
+    return out
+
+
 def propagate_ngcf(graph: CsrGraph, user_emb, item_emb, W_gc, W_bi):
     """``NGCF_Encoder.forward`` (model/NGCF.py:90-104).  Only the ``torch.sparse.mm`` of :95 is on
     the hot path; the dense d x d transforms and the leaky-relu stay library calls."""

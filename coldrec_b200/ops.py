@@ -228,6 +228,28 @@ def gather_rows(src: torch.Tensor, ids: torch.Tensor, out=None) -> torch.Tensor:
     return out
 
 
+def copy_rows(src: torch.Tensor, dst: torch.Tensor, src_ids=None, dst_ids=None) -> torch.Tensor:
+    """dst[dst_ids[j]] = src[src_ids[j]] (either id list may be None = j); ``dst_ids`` must not repeat.  In place on dst."""
+    lib = _lib.load()
+    src = _req(src, torch.float32, "src"); dst = _req(dst, torch.float32, "dst")
+    src_ids = _req(src_ids, torch.int32, "src_ids", optional=True); dst_ids = _req(dst_ids, torch.int32, "dst_ids", optional=True)
+    dev = _same_device(src, dst, src_ids, dst_ids)
+    if src.dim() != 2 or dst.dim() != 2 or src.shape[1] != dst.shape[1]:
+        raise ValueError(f"src {tuple(src.shape)} and dst {tuple(dst.shape)} must be 2-D tables of the same width")
+    counts = {t.numel() for t in (src_ids, dst_ids) if t is not None}
+    if len(counts) > 1:
+        raise ValueError("src_ids and dst_ids differ in length")
+    n = counts.pop() if counts else min(src.shape[0], dst.shape[0])
+    if (src_ids is None and n > src.shape[0]) or (dst_ids is None and n > dst.shape[0]):
+        raise ValueError("more rows to copy than the table without an id list holds")
+    if n == 0:
+        return dst
+    with torch.cuda.device(dev):
+        _lib.check(lib.cr_copy_rows_f32(_ptr(src), _ptr(src_ids), _ptr(dst_ids), n, src.shape[1], _ptr(dst), _stream(dev)),
+                   "cr_copy_rows_f32")
+    return dst
+
+
 # ------------------------------------------------------------------------------------------------ K2
 def dcg_tables(K: int):
     """1/log(n+2,2) and its running sums, computed with the reference's own expression and addition

@@ -154,6 +154,12 @@ CR_API int cr_fill_masked(float *out_score, int32_t *out_id, int64_t n_q, int K,
 /* dst[j,:] = src[ids[j],:]  — `self.user_emb[users]` (model/MF.py:62) and flag-compaction of item tables. */
 CR_API int cr_gather_rows_f32(const float *src, const int32_t *ids, int64_t n, int d, float *dst, void *stream);
 
+/* dst[dst_ids ? dst_ids[j] : j, :] = src[src_ids ? src_ids[j] : j, :]  — row overwrite between tables:
+ * `h[cold_rows] = item_x[cold_item_idx]` after every convolution of CGRC's frozen-cold propagation
+ * (model/CGRC.py:90-91), `item_emb[cold] = generated` (model/GAR.py:44-46).  dst_ids must not repeat. */
+CR_API int cr_copy_rows_f32(const float *src, const int32_t *src_ids, const int32_t *dst_ids, int64_t n, int d, float *dst,
+                            void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K2 — ranking metrics reduced on device.  Replaces `ranking_evaluation` / `Metric.*`
  * (util/evaluator.py:9-32, 47-63, 95-115, 153-187).

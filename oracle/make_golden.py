@@ -347,13 +347,46 @@ def golden_towers(work, name, data, user_emb, item_emb, seed):
     return out
 
 
+def golden_cgrc(seed):
+    """CGRC's and FSGNN's propagation variants (model/CGRC.py:64-93, model/FSGNN.py:433-442) on the adjacency and the
+    embeddings of the committed graph.npz: the layer list with cold item rows frozen at their content vector, the mean
+    over layers 0..L, and FSGNN's stack(dim=0).mean — all by the reference's own functions."""
+    import scipy.sparse as sp
+    import importlib
+    ref_cgrc = importlib.import_module("model.CGRC")         # `from model import CGRC` is the trainer class
+    FSGNN_Learner = importlib.import_module("model.FSGNN").FSGNN_Learner
+    g = dict(np.load(os.path.join(OUT, "graph.npz")))
+    n_u, n_i = int(g["user_num"]), int(g["item_num"])
+    adj = sp.csr_matrix((g["adj_data"], g["adj_indices"], g["adj_indptr"]), shape=(n_u + n_i, n_u + n_i))
+    adj_t = ref_cgrc._sparse_adj_tensor(adj, "cpu")
+    rng = np.random.default_rng(seed)
+    cold = np.sort(rng.choice(n_i, n_i // 5, replace=False)).astype(np.int64)
+    item_x = (rng.standard_normal((n_i, D)) * 0.1).astype(np.float32)          # content-projected item vectors x_i
+    U = torch.from_numpy(g["E0_user"])
+    out = {"cold_item_idx": cold, "item_x": item_x}
+    layers = ref_cgrc._propagate_gprime_frozen_cold(adj_t, U, torch.from_numpy(item_x), n_u, 3, torch.from_numpy(cold))
+    for k, h in enumerate(layers):
+        out[f"frozen_L{k}"] = h.numpy().copy()
+    layers0 = ref_cgrc._propagate_gprime_frozen_cold(adj_t, U, torch.from_numpy(item_x), n_u, 2, torch.zeros(0, dtype=torch.long))
+    out["frozen_nocold_L2"] = layers0[-1].numpy().copy()
+    zu, zi = ref_cgrc._lightgcn_mean_all_layers(adj_t, U, torch.from_numpy(item_x), n_u, 3)
+    out["mean_user"], out["mean_item"] = zu.numpy().copy(), zi.numpy().copy()
+    fake = types.SimpleNamespace(n_layers=2, adj_complete=adj_t)
+    fu, fi = FSGNN_Learner._lightgcn(fake, U, torch.from_numpy(item_x))
+    out["fsgnn_user"], out["fsgnn_item"] = fu.numpy().copy(), fi.numpy().copy()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default=None, choices=[None, "train"], help="regenerate a single fixture")
+    ap.add_argument("--only", default=None, choices=[None, "train", "cgrc"], help="regenerate a single fixture")
     only = ap.parse_args().only
     _import_reference()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)           # fixtures must not depend on thread-count-dependent blocking
+    if only == "cgrc":
+        np.savez_compressed(os.path.join(OUT, "cgrc.npz"), **golden_cgrc(15))
+        return
     with tempfile.TemporaryDirectory() as work:
         ev, data = golden_eval(work, "synitem", "item", 11, n_users=150, n_items=240, n_inter=4200, content_dim=24)
         np.savez_compressed(os.path.join(OUT, "train.npz"), **golden_train(data, 14))
@@ -361,6 +394,7 @@ def main():
             return
         np.savez_compressed(os.path.join(OUT, "eval_item.npz"), **ev)
         np.savez_compressed(os.path.join(OUT, "graph.npz"), **golden_graph(data, 12))
+        np.savez_compressed(os.path.join(OUT, "cgrc.npz"), **golden_cgrc(15))
         tw = golden_towers(work, "synitem", data, torch.from_numpy(ev["user_emb"]), torch.from_numpy(ev["item_emb"]), 13)
         np.savez_compressed(os.path.join(OUT, "towers.npz"), **tw)
         eu, _ = golden_eval(work, "synuser", "user", 21, n_users=160, n_items=130, n_inter=3000, content_dim=16, variants=False)

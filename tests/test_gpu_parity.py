@@ -403,3 +403,49 @@ def test_tc_raw_scores_are_tf32_products():
     exact = torch.topk(t(U) @ t(I).T, 20, dim=1)
     assert np.allclose(s.cpu().numpy(), exact.values.numpy(), atol=1e-5)
     assert np.array_equal(i.cpu().numpy().astype(np.int64), exact.indices.numpy())
+
+
+def test_cgrc_frozen_cold_and_fsgnn_propagation_vs_reference_golden():
+    """CGRC's frozen-cold layer list (model/CGRC.py:76-93), its mean over layers and FSGNN's _lightgcn (model/FSGNN.py:433-442)."""
+    import coldrec_b200 as cr
+    g, c = load_golden("graph"), load_golden("cgrc")
+    n_u, n_i = int(g["user_num"]), int(g["item_num"])
+    adj = sp.csr_matrix((g["adj_data"], g["adj_indices"], g["adj_indptr"]), shape=(n_u + n_i, n_u + n_i))
+    G = cr.CsrGraph.from_scipy(adj, DEV)
+    U, X = t(g["E0_user"]).to(DEV), t(c["item_x"]).to(DEV)
+    cold = t(c["cold_item_idx"]).to(DEV)
+    layers = cr.propagate_frozen_cold(G, U, X, 3, cold)
+    assert len(layers) == 4
+    for k, h in enumerate(layers):
+        ref = c[f"frozen_L{k}"]
+        assert np.abs(h.cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+        if k:
+            assert np.array_equal(h.cpu().numpy()[n_u + c["cold_item_idx"]], c["item_x"][c["cold_item_idx"]])
+    none = cr.propagate_frozen_cold(G, U, X, 2, torch.zeros(0, dtype=torch.int64, device=DEV))
+    assert np.abs(none[-1].cpu().numpy() - c["frozen_nocold_L2"]).max() <= 1e-5 * np.abs(c["frozen_nocold_L2"]).max()
+    for L, ku, ki in ((3, "mean_user", "mean_item"), (2, "fsgnn_user", "fsgnn_item")):
+        zu, zi = cr.propagate(G, U, X, L)
+        for got, ref in ((zu, c[ku]), (zi, c[ki])):
+            assert np.abs(got.cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+def test_copy_rows_gather_scatter_and_errors():
+    from coldrec_b200 import ops
+    rng = np.random.default_rng(5)
+    src = torch.from_numpy(rng.standard_normal((50, 32)).astype(np.float32)).to(DEV)
+    dst = torch.zeros((80, 32), device=DEV)
+    si = torch.from_numpy(rng.choice(50, 20, replace=False).astype(np.int32)).to(DEV)
+    di = torch.from_numpy(rng.choice(80, 20, replace=False).astype(np.int32)).to(DEV)
+    ops.copy_rows(src, dst, src_ids=si, dst_ids=di)
+    want = torch.zeros((80, 32), device=DEV)
+    want[di.long()] = src[si.long()]
+    assert torch.equal(dst, want)
+    out = ops.copy_rows(src, torch.zeros((20, 32), device=DEV), src_ids=si)               # pure gather
+    assert torch.equal(out, src[si.long()])
+    out = ops.copy_rows(src[:20].contiguous(), torch.zeros((80, 32), device=DEV), dst_ids=di)   # pure scatter
+    assert torch.equal(out[di.long()], src[:20])
+    with pytest.raises(ValueError):
+        ops.copy_rows(src, dst, src_ids=si, dst_ids=di[:5].contiguous())
+    with pytest.raises(ValueError):
+        ops.copy_rows(src, torch.zeros((80, 16), device=DEV))
+    assert ops.copy_rows(src, dst, src_ids=si[:0].contiguous(), dst_ids=di[:0].contiguous()) is dst

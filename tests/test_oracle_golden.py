@@ -1,6 +1,7 @@
 """The CPU oracle restatement vs. golden vectors produced by the UNMODIFIED reference."""
 import numpy as np
 import pytest
+import scipy.sparse as sp
 import torch
 
 from oracle import coldrec_oracle as O
@@ -210,3 +211,23 @@ def test_chunked_dense_eval_equals_unchunked():
         s1, i1 = O.evaluate_topk_dense_chunked(U, I, uids, rowptr, col, cm, 20, user_batch=37, item_chunk=777)
         assert np.allclose(s0, s1, atol=1e-6, rtol=0)
         assert (i0 == i1).mean() > 0.999
+
+
+def test_cgrc_fsgnn_propagation_variants_vs_reference_golden():
+    """model/CGRC.py:64-93 and model/FSGNN.py:433-442, outputs of the reference's own functions (oracle/make_golden.py --only cgrc)."""
+    g, c = load_golden("graph"), load_golden("cgrc")
+    n_u, n_i = int(g["user_num"]), int(g["item_num"])
+    adj = sp.csr_matrix((g["adj_data"], g["adj_indices"], g["adj_indptr"]), shape=(n_u + n_i, n_u + n_i))
+    U, X = t(g["E0_user"]), t(c["item_x"])
+    layers = O.propagate_frozen_cold(adj, U, X, 3, c["cold_item_idx"])
+    assert len(layers) == 4
+    for k, h in enumerate(layers):
+        assert np.abs(h.numpy() - c[f"frozen_L{k}"]).max() <= 1e-7
+        if k:
+            assert np.array_equal(h.numpy()[n_u + c["cold_item_idx"]], c["item_x"][c["cold_item_idx"]])
+    none = O.propagate_frozen_cold(adj, U, X, 2, np.zeros(0, dtype=np.int64))
+    assert np.abs(none[-1].numpy() - c["frozen_nocold_L2"]).max() <= 1e-7
+    zu, zi = O.propagate(adj, U, X, 3)                     # CGRC._lightgcn_mean_all_layers == the LightGCN encoder
+    assert np.abs(zu.numpy() - c["mean_user"]).max() <= 1e-7 and np.abs(zi.numpy() - c["mean_item"]).max() <= 1e-7
+    fu, fi = O.propagate(adj, U, X, 2)                     # FSGNN._lightgcn: stack(dim=0).mean(dim=0), 2 layers
+    assert np.abs(fu.numpy() - c["fsgnn_user"]).max() <= 1e-7 and np.abs(fi.numpy() - c["fsgnn_item"]).max() <= 1e-7
