@@ -390,7 +390,7 @@ def run_lightgcn(args, device, rank, world, pk, pk_src, lib):
                        "parallelism": f"row-partitioned x{world}, {exchange}" if world > 1 else "single GPU",
                        "l2": "embedding table %.1f GB >> L2; no flush" % (N * D * 4 / 2**30)},
                gpu_launches=int(launches),
-               roofline={"bound": "hbm", "kernel": "spmm_rows_kernel (+ long-row split kernels)", "achieved": round(step_gbs, 1),
+               roofline={"bound": "hbm", "kernel": "spmm_rows_grouped_kernel (rows + long-row chunks in one launch; + spmm_long_reduce_kernel)", "achieved": round(step_gbs, 1),
                          "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(step_gbs / pk["hbm_gbs"], 4),
                          "traffic": ncu_traffic("spmm_rows_grouped_kernel_bytes_per_launch") if (world == 1 and args.graph_edges == GRAPH_EDGES) else None,
                          "peak_source": f"{pk_src} hbm_gbs (copy bandwidth)", "bytes_per_layer": bytes_layer,
