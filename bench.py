@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 N_USERS, N_ITEMS, D, K, TOPN = 1_000_000, 10_000_000, 64, 20, [10, 20]
 USERS_PER_STEP = 75_776          # 296 query tiles of 256 = two full waves of 148 SMs
 MASK_PER_USER, GT_PER_USER = 100, 10
+MAX_DISTINCT_PLANS = 12           # distinct synthetic eval batches kept resident (device + pinned host); longer runs cycle through them
 GRAPH_EDGES, LAYERS = 100_000_000, 3
 
 
@@ -211,8 +212,13 @@ def run_b200(args):
         ib, ie = scorer.item_range(args.n_items)
         gi = torch.Generator(device=device).manual_seed(1000 + scorer.ishard)    # replicas of a shard hold the same rows
         item_shard = torch.randn(ie - ib, D, device=device, generator=gi) * 0.125
-        plans_d = make_step_plans(W + Ksteps, n_q, args.n_users, args.n_items, 6, device)
-        plans = [EvalPlan.from_arrays(**p) for p in plans_d]
+        # every step ranks a different batch of users; beyond MAX_DISTINCT_PLANS the batches repeat (a long --steps run would
+        # otherwise pin W+K x 35 MB x N of host memory per rank) — each step still copies and sweeps its whole plan
+        n_distinct = min(W + Ksteps, MAX_DISTINCT_PLANS)
+        distinct = make_step_plans(n_distinct, n_q, args.n_users, args.n_items, 6, device)
+        plans_d = [distinct[k % n_distinct] for k in range(W + Ksteps)]
+        distinct_plans = [EvalPlan.from_arrays(**p) for p in distinct]
+        plans = [distinct_plans[k % n_distinct] for k in range(W + Ksteps)]
 
         def step(plan):
             s, i = scorer.topk(user_tab, item_shard, ib, plan)
@@ -251,7 +257,8 @@ def run_b200(args):
 
         # end to end through the host-buffer API: H2D of the step's plan from pinned memory, D2H of top-K + metric sums
         hb = HostBatchEvaluator(scorer, TOPN, n_q, n_q * MASK_PER_USER, n_q * GT_PER_USER, device)
-        host_plans = [hb.pin(p) for p in plans_d[W:]]
+        pinned = [hb.pin(p) for p in distinct]
+        host_plans = [pinned[k % n_distinct] for k in range(W, W + Ksteps)]
         hb.run(user_tab, item_shard, ib, host_plans[0])
         barrier(world, device)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -279,7 +286,7 @@ def run_b200(args):
                           "n_refined_last_step": int(scorer.last_n_refined.item()) if scorer.last_n_refined is not None else None})
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_score_baseline(user_tab, item_shard, plans_d[W], args.cpu_sample_users)
-        del item_shard, plans, plans_d, host_plans, hb
+        del item_shard, plans, plans_d, host_plans, hb, distinct, distinct_plans, pinned
         torch.cuda.empty_cache()
 
     if args.workload in ("both", "lightgcn"):
