@@ -244,6 +244,8 @@ class RowPartitionedGraph:
         # p gathers row r in the next layer.  Item rows of a bipartite graph mostly have a handful of nonzeros, hence a
         # handful of readers; only user rows (~100 nonzeros) are read everywhere.
         self._need = self._seg_of_local = None
+        self._need_last = {}            # replicate_result -> need mask of the last layer
+        self.need_copies = float(self.world)          # mean number of GPUs that read a row (W = dense all-gather)
         if 1 < self.world <= 8 and self.n:
             need = np.zeros(self.n, dtype=np.uint8)
             for r, pr in enumerate(parts):
@@ -345,7 +347,7 @@ class RowPartitionedGraph:
         need_last = None
         if replicate_result is not None and self._need is not None:
             key = tuple(sorted(replicate_result))
-            cache = self.__dict__.setdefault("_need_last", {})
+            cache = self._need_last
             if key not in cache:
                 m = np.full(nl, 1 << self.rank, dtype=np.uint8)
                 m[np.isin(self._seg_of_local, key)] = (1 << W) - 1
