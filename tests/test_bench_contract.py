@@ -1,0 +1,52 @@
+"""bench.py's one-line JSON contract: the CPU reference arm here (no GPU needed), the B200 arm at toy sizes on the GPU box."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+             "dtype", "data", "config", "e2e", "gpu_launches"}
+
+
+def _run(args, env=None, timeout=600):
+    e = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        e.pop(k, None)
+    e.update(env or {})
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True, env=e, timeout=timeout, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+
+
+def test_reference_arm_line_and_non_zero_ranks_stay_silent():
+    small = ["--impl", "reference", "--steps", "2", "--warmup", "1", "--n-items", "30000", "--n-users", "4000", "--cpu-sample-users", "8"]
+    (line,) = _run(small)
+    assert BASE_KEYS <= set(line) and line["impl"] == "reference"
+    assert line["unit"] == "users/s" and line["higher_is_better"] is True and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["steps"] == 2 and line["warmup"] == 1 and line["n_gpus"] == 1
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "8 users/step" in cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
+    # under torchrun only rank 0 runs the CPU arm; the other ranks exit 0 without a line
+    assert _run(small, env={"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}) == []
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_b200_arm_line_at_toy_sizes():
+    (line,) = _run(["--steps", "3", "--warmup", "3", "--n-items", "300000", "--n-users", "60000", "--users-per-step", "4096",
+                    "--graph-edges", "3000000", "--cpu-sample-users", "16", "--train-batch", "1024"])
+    assert BASE_KEYS <= set(line) and "impl" not in line
+    assert line["unit"] == "users/s" and line["value"] > 0 and line["gpu_launches"] > 0 and line["vs_baseline"] is None
+    assert line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    for part in (line, line["lightgcn"]):
+        r = part["roofline"]
+        assert r["bound"] in ("hbm", "tensor") and r["achieved"] > 0 and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
+        assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(part["clocks"])
+        assert part["cpu_baseline"]["kind"] == "port" and part["cpu_baseline"]["value"] > 0
+    assert line["lightgcn"]["unit"] == "edges/s" and line["lightgcn"]["gpu_launches"] > 0
+    assert line["lightgcn"]["train_step"]["value"] > 0
