@@ -377,15 +377,43 @@ def golden_cgrc(seed):
     return out
 
 
+def golden_disk(work):
+    """The reference's ON-DISK layout for a tiny dataset, written by its own scripts (data/split.py, data/convert.py) from the
+    same seeded interactions as eval_tiny.npz: data/<ds>/cold_item/{warm_train,warm_val,...}.csv + info_dict.pkl and
+    data/<ds>/<ds>_item_content.npy (main.py:28-52), plus what the reference's loaders + ColdStartDataBuilder make of it."""
+    import shutil
+    name, cold_object = "syntiny", "item"
+    rng = np.random.default_rng(31)
+    prepare_dataset(work, name, cold_object, rng, n_users=40, n_items=36, n_inter=420, content_dim=8)
+    data, splits, info, content = load_config(work, name, cold_object)
+    dst = os.path.join(OUT, "disk", "data", name)
+    shutil.rmtree(os.path.join(OUT, "disk"), ignore_errors=True)
+    shutil.copytree(os.path.join(work, "data", name, f"cold_{cold_object}"), os.path.join(dst, f"cold_{cold_object}"))
+    shutil.copy(os.path.join(work, "data", name, f"{name}_{cold_object}_content.npy"), dst)
+    expect = dict(id2user=np.array([data.id2user[i] for i in range(len(data.user))]),
+                  id2item=np.array([data.id2item[i] for i in range(len(data.item))]),
+                  mapped_warm_item_idx=np.asarray(data.mapped_warm_item_idx), mapped_cold_item_idx=np.asarray(data.mapped_cold_item_idx),
+                  mapped_warm_user_idx=np.asarray(data.mapped_warm_user_idx), mapped_cold_user_idx=np.asarray(data.mapped_cold_user_idx),
+                  mapped_item_content=np.asarray(data.mapped_item_content)[:len(data.item)],
+                  norm_adj_indptr=data.norm_adj.tocsr().indptr, norm_adj_indices=data.norm_adj.tocsr().indices,
+                  norm_adj_data=data.norm_adj.tocsr().data, user_num=np.array(data.user_num), item_num=np.array(data.item_num),
+                  n_train=np.array(len(data.training_data)))
+    np.savez_compressed(os.path.join(OUT, "disk", "expect.npz"), **expect)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default=None, choices=[None, "train", "cgrc"], help="regenerate a single fixture")
+    ap.add_argument("--only", default=None, choices=[None, "train", "cgrc", "disk"], help="regenerate a single fixture")
     only = ap.parse_args().only
     _import_reference()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)           # fixtures must not depend on thread-count-dependent blocking
     if only == "cgrc":
         np.savez_compressed(os.path.join(OUT, "cgrc.npz"), **golden_cgrc(15))
+        return
+    if only == "disk":
+        with tempfile.TemporaryDirectory() as work:
+            golden_disk(work)
         return
     with tempfile.TemporaryDirectory() as work:
         ev, data = golden_eval(work, "synitem", "item", 11, n_users=150, n_items=240, n_inter=4200, content_dim=24)
@@ -402,6 +430,8 @@ def main():
         # fewer unmasked candidates than K in the 'cold' setting: masked ids must appear in the lists
         et, _ = golden_eval(work, "syntiny", "item", 31, n_users=40, n_items=36, n_inter=420, content_dim=8, variants=False)
         np.savez_compressed(os.path.join(OUT, "eval_tiny.npz"), **et)
+    with tempfile.TemporaryDirectory() as work:
+        golden_disk(work)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -107,3 +107,31 @@ def test_accepts_arrays_and_empty_splits():
     c = ArrayDataBuilder(*args)
     e = c.eval_arrays("cold_valid")
     assert len(e["user_ids"]) == 0 and e["mask_rowptr"].tolist() == [0] and e["gt_rowptr"].tolist() == [0]
+
+
+def test_from_disk_reads_the_reference_layout_unchanged():
+    """tests/golden/disk/ was written by the reference's own data/split.py + data/convert.py; expect.npz is what its
+    DataLoader + ColdStartDataBuilder make of it (oracle/make_golden.py --only disk)."""
+    import os
+    import scipy.sparse as sp
+    from coldrec_b200.databuilder import ArrayDataBuilder, load_data_set
+    from tests.helpers import GOLDEN
+    root = os.path.join(GOLDEN, "disk")
+    e = dict(np.load(os.path.join(root, "expect.npz")))
+    pairs = load_data_set(os.path.join(root, "data", "syntiny", "cold_item", "warm_train.csv"))
+    assert pairs.dtype == np.int64 and pairs.shape == (int(e["n_train"]), 2)
+    b = ArrayDataBuilder.from_disk("syntiny", "item", root=root)
+    assert (b.user_num, b.item_num) == (int(e["user_num"]), int(e["item_num"]))
+    assert np.array_equal(np.array([b.id2user[i] for i in range(len(b.user))]), e["id2user"])
+    assert np.array_equal(np.array([b.id2item[i] for i in range(len(b.item))]), e["id2item"])
+    for k in ("mapped_warm_item_idx", "mapped_cold_item_idx", "mapped_warm_user_idx", "mapped_cold_user_idx"):
+        assert np.array_equal(np.asarray(getattr(b, k)), e[k]), k
+    assert np.array_equal(b.mapped_item_content[:len(b.item)], e["mapped_item_content"])
+    adj = b.norm_adj.tocsr(); adj.sort_indices()
+    ref = sp.csr_matrix((e["norm_adj_data"], e["norm_adj_indices"], e["norm_adj_indptr"]), shape=adj.shape); ref.sort_indices()
+    assert np.array_equal(adj.indptr, ref.indptr) and np.array_equal(adj.indices, ref.indices)
+    assert np.abs(adj.data - ref.data).max() <= 1e-7
+    with pytest.raises(ValueError):
+        ArrayDataBuilder.from_disk("syntiny", "both", root=root)
+    with pytest.raises(FileNotFoundError):
+        ArrayDataBuilder.from_disk("nosuch", "item", root=root)
