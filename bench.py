@@ -286,6 +286,7 @@ def run_b200(args):
                           "n_refined_last_step": int(scorer.last_n_refined.item()) if scorer.last_n_refined is not None else None})
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_score_baseline(user_tab, item_shard, plans_d[W], args.cpu_sample_users)
+            out["gpu_library_baseline"] = library_score_baseline(user_tab, item_shard, plans_d[W])
         del item_shard, plans, plans_d, host_plans, hb, distinct, distinct_plans, pinned
         torch.cuda.empty_cache()
 
@@ -406,6 +407,8 @@ def run_lightgcn(args, device, rank, world, pk, pk_src, lib):
                clocks=clk.summary())
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_spmm_baseline(G, E0u, E0i)
+        out["gpu_library_baseline"] = library_spmm_baseline(G, E0u, E0i)
+        torch.cuda.empty_cache()
     if world == 1 and not args.no_train:
         out["train_step"] = run_train_step(args, device, G, E0u, E0i, pk, lib)
     return out
@@ -450,6 +453,65 @@ def run_train_step(args, device, G, E0u, E0i, pk, lib):
             "roofline": {"bound": "hbm", "achieved": round(step_bytes / (ms * 1e-3) / 1e9, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": round(step_bytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4), "bytes_per_step": step_bytes},
             "loss": [round(x, 6) for x in loss.cpu().tolist()[:3]], "sampler_exhausted": int(smp.n_exhausted.item())}
+
+
+# ------------------------------------------------------------------------------------------- the reference's GPU path
+def _event_ms(fn, iters=3, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def library_score_baseline(user_tab, item_tab, plan_d, batch=512):
+    """What ColdRec itself runs with --use_gpu true ("existing Blackwell library path"): torch.matmul with TF32
+    off (model/MF.py:62), the per-user index_put mask loop (model/BaseRecommender.py:175-177) and torch.topk (:182), on one
+    batch of this step's users.  Reported next to the CPU baseline, never part of the product path."""
+    try:
+        users = plan_d["user_ids"][:batch].long()
+        rp = plan_d["mask_rowptr"][:batch + 1].tolist()
+        rated = [plan_d["mask_col"][rp[j]:rp[j + 1]].long() for j in range(batch)]
+
+        def one_batch():
+            cand = torch.matmul(user_tab[users], item_tab.transpose(0, 1))
+            for j in range(batch):
+                cand[j, rated[j]] = -10e8
+            return torch.topk(cand, K, dim=1, largest=True, sorted=True)
+        ms = _event_ms(one_batch)
+        return {"value": round(batch / ms * 1e3, 1), "unit": "users/s", "kind": "reference torch ops on this GPU",
+                "sample": f"{batch}-user batches x {item_tab.shape[0]} items (matmul fp32 + index_put loop + topk), {ms:.1f} ms per batch"}
+    except Exception as ex:      # e.g. out of memory on a smaller GPU: the bench line must still come out
+        torch.cuda.empty_cache()
+        return {"error": f"{type(ex).__name__}: {str(ex)[:120]}"}
+
+
+def library_spmm_baseline(G, E0u, E0i):
+    """torch.sparse.mm on the coalesced int64 COO tensor (util/databuilder.py:959-962, model/LightGCN.py:86-96) + stack + mean."""
+    try:
+        N = G.n_rows
+        rows = torch.repeat_interleave(torch.arange(N, device=G.col.device), G.rowptr[1:] - G.rowptr[:-1])
+        A = torch.sparse_coo_tensor(torch.stack([rows, G.col.long()]), G.val, (N, N)).coalesce()
+        del rows
+        E0 = torch.cat([E0u, E0i])
+
+        def forward():
+            ego, layers = E0, [E0]
+            for _ in range(LAYERS):
+                ego = torch.sparse.mm(A, ego)
+                layers.append(ego)
+            return torch.mean(torch.stack(layers, dim=1), dim=1)
+        ms = _event_ms(forward)
+        return {"value": round(G.nnz * LAYERS / ms * 1e3, 1), "unit": "edges/s", "kind": "reference torch ops on this GPU",
+                "sample": f"torch.sparse.mm (COO int64) x {LAYERS} + stack + mean, {ms:.1f} ms per propagation"}
+    except Exception as ex:
+        torch.cuda.empty_cache()
+        return {"error": f"{type(ex).__name__}: {str(ex)[:120]}"}
 
 
 # ------------------------------------------------------------------------------------------- CPU arms (oracle port)
