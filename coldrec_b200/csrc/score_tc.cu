@@ -38,10 +38,24 @@ namespace {
 
 constexpr int kD = 64;                  // embedding width served by this path
 constexpr int kBM = 256;                // queries per unit (2 x 128-row MMA tiles)
-constexpr int kBN = 96;                 // items per tile
+// Tile geometry knobs (tools/build_variant.sh): 512 TMEM columns = 128 (queries) + kAcc x 2 x kBN, so the alternatives to
+// 96-item tiles x 2 accumulator stages are 64 x 3 (a third stage decouples the MMA issuer from the slowest epilogue warp —
+// the lever DESIGN.md K1 names for short shards; untested at the time of writing) and 32 x 6.
+#ifndef CR_TC_BN
+#define CR_TC_BN 96
+#endif
+#ifndef CR_TC_ACC
+#define CR_TC_ACC 2
+#endif
+#ifndef CR_TC_STAGES
+#define CR_TC_STAGES 6
+#endif
+constexpr int kBN = CR_TC_BN;           // items per tile
 constexpr int kChunks = kBN / 32;       // 32-column epilogue chunks per tile
-constexpr int kStages = 6;              // item smem ring
-constexpr int kAcc = 2;                 // TMEM accumulator stages
+constexpr int kStages = CR_TC_STAGES;   // item smem ring
+constexpr int kAcc = CR_TC_ACC;         // TMEM accumulator stages
+static_assert(kBN % 32 == 0 && kBN >= 32 && 128 + kAcc * 2 * kBN <= 512, "TMEM: 128 query columns + kAcc x 2 x kBN accumulator columns");
+static_assert(8 * kChunks <= 32, "the mask producer's dirty-word bitmap holds 8 queries x kChunks bits per lane");
 #ifndef CR_MASK_STAGES
 #define CR_MASK_STAGES 4
 #endif
