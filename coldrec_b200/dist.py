@@ -183,13 +183,20 @@ class RowPartitionedGraph:
     """
 
     def __init__(self, rowptr: np.ndarray, col: np.ndarray, val: Optional[np.ndarray], device, group=None,
-                 spmm: Optional[Callable] = None, segments: Optional[Sequence[int]] = None):
+                 spmm: Optional[Callable] = None, segments: Optional[Sequence[int]] = None,
+                 rank: Optional[int] = None, world: Optional[int] = None, symmetric_alloc: Optional[Callable] = None):
         """``segments`` = row counts of consecutive row classes (for the bipartite adjacency: (user_num,
         item_num)); each class is split by nonzeros on its own and rank r owns part r of every class, which
-        balances rows *and* nonzeros (user rows carry ~10x the nonzeros of item rows)."""
+        balances rows *and* nonzeros (user rows carry ~10x the nonzeros of item rows).  ``rank`` / ``world`` override the
+        process group's (one process driving several partitions); ``symmetric_alloc(shape) -> (tensor, handle)`` replaces
+        the torch symmetric-memory allocation of the peer-store path (the handle needs ``buffer_ptrs_dev``, ``barrier()``
+        and optionally ``multicast_ptr``) — both exist for the CPU emulation in tests/test_dist_gloo.py."""
         self.group = group
         on = dist.is_available() and dist.is_initialized()
         self.rank, self.world = (dist.get_rank(group), dist.get_world_size(group)) if on else (0, 1)
+        if rank is not None and world is not None:
+            self.rank, self.world = int(rank), int(world)
+        self._symmetric_alloc = symmetric_alloc
         rowptr = np.asarray(rowptr)
         self.n = len(rowptr) - 1
         segments = list(segments) if segments is not None else [self.n]
@@ -294,13 +301,18 @@ class RowPartitionedGraph:
         """Allocate three symmetric (peer-mapped) padded tables [W*rows_pad, d]: two ping-pong gather sources and
         one for the finished layer mean.  Uses torch symmetric memory only as the allocator / pointer exchange /
         inter-GPU barrier; the data movement is done by the SpMM kernel's own epilogue stores."""
-        import torch.distributed._symmetric_memory as symm_mem
         dev = self.local.rowptr.device
-        group = self.group if self.group is not None else dist.group.WORLD
         self._p2p_d, self._xbuf, self._xhdl = d, [], []
+        shape = (self.world * self.rows_pad, d)
         for _ in range(3):
-            t = symm_mem.empty((self.world * self.rows_pad, d), dtype=torch.float32, device=dev)
-            self._xhdl.append(symm_mem.rendezvous(t, group=group))
+            if self._symmetric_alloc is not None:
+                t, h = self._symmetric_alloc(shape)
+            else:
+                import torch.distributed._symmetric_memory as symm_mem
+                group = self.group if self.group is not None else dist.group.WORLD
+                t = symm_mem.empty(shape, dtype=torch.float32, device=dev)
+                h = symm_mem.rendezvous(t, group=group)
+            self._xhdl.append(h)
             self._xbuf.append(t)
         self.has_multicast = all(int(getattr(h, "multicast_ptr", 0) or 0) != 0 for h in self._xhdl)
 
@@ -340,7 +352,7 @@ class RowPartitionedGraph:
                 if include_ego:
                     acc[o:o + (e - b)].copy_(E0[b:e])
                 o += e - b
-        plan = self.local.plan(E0.shape[1])
+        plan = self.local.plan(E0.shape[1]) if self.local.rowptr.is_cuda else None      # (CPU: emulated kernel, no plan)
         rowptr = self.local.rowptr[:nl + 1]  # the padding rows are empty and nobody gathers them: not computed, not sent
         scatter = (not padded_io) and len(mine) <= 2
         need = self._need if sparse else None

@@ -306,6 +306,112 @@ def test_grid_sharded_scoring(world):
     assert grid_item_shards(8, 10_000_000, 1) == 8 and grid_item_shards(8, 100, 1000) == 1 and grid_item_shards(6, 900, 250) == 3
 
 
+class _FakeSymmetric:
+    """Stand-in for torch symmetric memory in ONE process: buffer k of every rank is registered under the same key, a
+    barrier is a threading.Barrier.  `buffer_ptrs_dev` is the key the emulated kernel uses to find the peers' tables."""
+
+    def __init__(self, world):
+        import threading
+        self.world, self.tables, self.bar = world, {}, threading.Barrier(world)
+        self.count = [0] * world
+
+    def allocator(self, rank):
+        def alloc(shape):
+            key = self.count[rank]
+            self.count[rank] += 1
+            t = torch.full(shape, float("nan"), dtype=torch.float32)
+            self.tables.setdefault(key, {})[rank] = t
+            outer = self
+
+            class H:
+                buffer_ptrs_dev, multicast_ptr = key, 0
+
+                def barrier(self_inner):
+                    outer.bar.wait()
+            return t, H()
+        return alloc
+
+
+def _emulated_spmm_bcast(fake):
+    """cr_spmm_csr_bcast_f32 in numpy, store_epilogue semantics included (coldrec_b200/csrc/spmm.cu): y = A_local X;
+    acc = (beta * acc + y) / div; row r goes to destination row off + r (r < split) or off_hi + r, on the peers whose need bit
+    is set (all peers without a mask); with bcast_acc the peers receive acc instead of y."""
+    def spmm_bcast(rowptr, col, val, X, peer_tables_dev, n_peers, peer_row_offset, acc=None, acc_in=None, acc_beta=1.0, acc_div=1.0,
+                   plan=None, bcast_acc=False, peer_row_split=None, peer_row_offset_hi=0, peer_need=None, multicast_ptr=0):
+        n = rowptr.numel() - 1
+        nnz = int(rowptr[-1])
+        A = sp.csr_matrix((val.numpy()[:nnz], col.numpy()[:nnz], rowptr.numpy()), shape=(n, X.shape[0]))
+        Xn = X.numpy()
+        assert not np.isnan(Xn[np.unique(col.numpy()[:nnz])]).any(), "gathered a row that was never delivered to this rank"
+        y = torch.from_numpy((A @ np.nan_to_num(Xn)).astype(np.float32))
+        out = y
+        if acc is not None:
+            src = acc_in if acc_in is not None else acc
+            res = ((acc_beta * src[:n] + y) if acc_beta else y) / acc_div
+            acc[:n] = res
+            if bcast_acc:
+                out = res
+        split = n if peer_row_split is None else peer_row_split
+        r = np.arange(n)
+        dest = torch.from_numpy(np.where(r < split, peer_row_offset + r, peer_row_offset_hi + r))
+        need = peer_need.numpy()[:n] if peer_need is not None else np.full(n, (1 << n_peers) - 1)
+        for p_ in range(n_peers):
+            sel = torch.from_numpy(np.nonzero((need >> p_) & 1)[0])
+            fake.tables[peer_tables_dev][p_][dest[sel]] = out[sel]
+        return acc
+    return spmm_bcast
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_peer_store_propagation_host_logic_emulated(world, monkeypatch):
+    """RowPartitionedGraph.propagate_p2p on CPU with the kernel and symmetric memory emulated (one thread per rank): need masks,
+    first layer read in place, ping-pong tables, last-layer scatter into the reference numbering (two ranges per rank),
+    users-only result replication — for 2, 4 and 8 ranks (the GPU test covers 2)."""
+    import threading
+    from coldrec_b200 import dist as crd
+    c = _case()
+    adj = O.normalize_graph_mat(O.bipartite_adjacency(c["eu"], c["ei"], c["n_users"], c["n_items"])).tocsr()
+    adj.sort_indices()
+    Ut, It = torch.from_numpy(c["U"]), torch.from_numpy(c["I"])
+    E0 = torch.cat([Ut, It])
+    fake = _FakeSymmetric(world)
+    monkeypatch.setattr(crd.ops, "spmm_bcast", _emulated_spmm_bcast(fake))
+    graphs = [crd.RowPartitionedGraph(adj.indptr.astype(np.int64), adj.indices.astype(np.int64), adj.data.astype(np.float32), "cpu",
+                                      segments=(c["n_users"], c["n_items"]), rank=r, world=world, symmetric_alloc=fake.allocator(r))
+              for r in range(world)]
+    results, errors = {}, []
+
+    def run(r):
+        try:
+            G = graphs[r]
+            results[r] = dict(full=G.propagate_p2p(E0, 3).numpy().copy(),
+                              noego=G.propagate_p2p(E0, 2, include_ego=False).numpy().copy(),
+                              dense=G.propagate_p2p(E0, 3, sparse=False).numpy().copy(),
+                              one=G.propagate_p2p(E0, 1).numpy().copy(),
+                              users=G.propagate_p2p(E0, 3, replicate_result=(0,)).numpy().copy(),
+                              padded=G.from_padded(G.propagate_p2p(G.to_padded(E0), 3, padded_io=True)).numpy().copy())
+        except Exception as ex:          # a dead thread would leave the others waiting at the barrier
+            errors.append((r, repr(ex)))
+            fake.bar.abort()
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t_.start() for t_ in threads]
+    [t_.join(timeout=120) for t_ in threads]
+    assert not errors, errors
+    ref = {L: torch.cat(O.propagate(adj, Ut, It, L)).numpy() for L in (1, 3)}
+    ref_noego = torch.cat(O.propagate(adj, Ut, It, 2, include_ego=False)).numpy()
+    tol = lambda want: 1e-5 * np.abs(want).max()
+    for r in range(world):
+        for key, want in (("full", ref[3]), ("dense", ref[3]), ("padded", ref[3]), ("one", ref[1]), ("noego", ref_noego)):
+            got = results[r][key]
+            assert not np.isnan(got).any(), f"rank {r} {key}: rows missing from the result"
+            assert np.abs(got - want).max() <= tol(want), f"rank {r} {key}"
+        (ub, ue), (ib, ie) = graphs[r].parts[r]
+        got = results[r]["users"]
+        for lo_, hi_ in ((0, c["n_users"]), (ib, ie)):          # user rows everywhere, item rows with their owner
+            assert np.abs(got[lo_:hi_] - ref[3][lo_:hi_]).max() <= tol(ref[3]), f"rank {r} users-only rows [{lo_},{hi_})"
+    assert graphs[0].need_copies < world
+
+
 def test_partition_helpers():
     from coldrec_b200.dist import partition_rows_by_nnz, shard_range
     assert [shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
