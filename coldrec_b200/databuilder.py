@@ -238,8 +238,8 @@ class ArrayDataBuilder:
             return out
         return self._memo("training_set_uid", make)
 
-    def training_size(self):                                        # :307-308
-        return len(np.unique(self.train_user)), len(np.unique(self.train_item)), len(self.train_user)
+    def training_size(self):                                        # :307-308: the whole id tables (cold entities included)
+        return len(self._users), len(self._items), len(self.train_user)
 
     def _split_size(self, split):
         u, i = self._dense[split]

@@ -122,6 +122,23 @@ def grid_item_shards(world: int, n_items: int, min_shard_items: int) -> int:
     return best
 
 
+_SUBGROUPS = {}      # (id of the parent group, S) -> list of sub-groups, created once per process and reused by every scorer
+
+
+def _user_group_subgroups(group, S: int):
+    """The W/S process groups of S consecutive ranks each.  ``dist.new_group`` is collective over the DEFAULT group, so a
+    proper sub-group as parent would hang (ranks outside it never make the call): the parent must be WORLD.  The groups are
+    cached — constructing a scorer per evaluation must not leak a communicator each time."""
+    if group is not None and group is not dist.group.WORLD and dist.get_world_size(group) != dist.get_world_size():
+        raise ValueError("GridShardedFullRankScorer with 1 < item_shards < world needs the default (WORLD) process group: "
+                         "torch.distributed.new_group is collective over all ranks")
+    key = (id(dist.group.WORLD), int(S))      # a re-initialised default group gets fresh sub-groups
+    if key not in _SUBGROUPS:
+        world = dist.get_world_size()
+        _SUBGROUPS[key] = [dist.new_group(ranks=list(range(g_ * S, (g_ + 1) * S))) for g_ in range(world // S)]
+    return _SUBGROUPS[key]
+
+
 class GridShardedFullRankScorer(ShardedFullRankScorer):
     """Item shards x user groups.  The W ranks form W/S user groups of S ranks; inside a group the item catalogue is split
     S ways exactly as in ``ShardedFullRankScorer`` (local top-K, NCCL all-gather of the (score, id) candidates inside the
@@ -142,11 +159,7 @@ class GridShardedFullRankScorer(ShardedFullRankScorer):
         self.ugroup, self.ishard = self.rank // S, self.rank % S
         self.sub = None
         if self.world > 1 and 1 < S < self.world:
-            base = dist.get_process_group_ranks(group) if group is not None else list(range(self.world))
-            for g_ in range(self.n_groups):          # every rank creates every subgroup, in the same order
-                h = dist.new_group(ranks=[base[g_ * S + k] for k in range(S)])
-                if g_ == self.ugroup:
-                    self.sub = h
+            self.sub = _user_group_subgroups(group, S)[self.ugroup]
         elif S == self.world:
             self.sub = group
 

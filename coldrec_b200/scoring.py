@@ -8,6 +8,7 @@ per-item flag byte (bit 0 = cold item, bit 1 = warm item).  ``FullRankScorer`` r
 """
 from __future__ import annotations
 
+import itertools
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -44,6 +45,21 @@ def _csr_from_lists(rows: Sequence[np.ndarray]):
     return rowptr, col
 
 
+def _csr_from_dicts(rows: Sequence[Dict], imap: Dict):
+    """CSR of dense item ids, ascending within a row, from one {raw_item: rating} dict per row: one pass over the
+    flattened keys through ``imap`` and one lexsort, instead of a numpy sort per user."""
+    lens = np.fromiter((len(r) for r in rows), dtype=np.int64, count=len(rows))
+    rowptr = np.zeros(len(rows) + 1, dtype=np.int64)
+    np.cumsum(lens, out=rowptr[1:])
+    total = int(rowptr[-1])
+    try:
+        flat = np.fromiter(map(imap.__getitem__, itertools.chain.from_iterable(rows)), dtype=np.int64, count=total)
+    except KeyError as e:              # util/databuilder.py:283-287
+        raise Exception(f"item {e.args[0]} not in current id table")
+    rowid = np.repeat(np.arange(len(rows), dtype=np.int64), lens)
+    return rowptr, flat[np.lexsort((flat, rowid))].astype(np.int32)
+
+
 @dataclass
 class EvalPlan:
     users: list                    # raw eval-user ids in ground-truth dict order (BaseRecommender.py:115)
@@ -67,14 +83,10 @@ class EvalPlan:
             uids = np.fromiter((umap[u] for u in users), dtype=np.int32, count=len(users))
         except KeyError as e:          # util/databuilder.py:289-296
             raise Exception(f"user {e.args[0]} not in current id table")
-        mask_rows, gt_rows = [], []
-        for u in users:
-            tr = data.training_set_u[u] if u in data.training_set_u else {}
-            mask_rows.append(np.sort(np.fromiter((imap[i] for i in tr), dtype=np.int64, count=len(tr))))
-            g = data_set[u]
-            gt_rows.append(np.sort(np.fromiter((imap[i] for i in g), dtype=np.int64, count=len(g))))
-        mrp, mc = _csr_from_lists(mask_rows)
-        grp, gc = _csr_from_lists(gt_rows)
+        tr = data.training_set_u
+        empty = {}
+        mrp, mc = _csr_from_dicts([tr[u] if u in tr else empty for u in users], imap)      # `in` first: never grows a defaultdict
+        grp, gc = _csr_from_dicts([data_set[u] for u in users], imap)
         t = lambda a: torch.from_numpy(a).to(device)
         return cls(users, t(uids), t(mrp), t(mc), t(grp), t(gc), flag_exclude_for(cold_object, data_type))
 
@@ -110,19 +122,23 @@ class FullRankScorer:
 
     def __init__(self, K: int, precision: int = ops.SCORE_TF32_CHECKED):
         self.K, self.precision = int(K), precision
-        self._compact_cache = {}
+        self._gid_cache = {}                         # (flags identity, group, excl) -> kept item ids; never table contents
         self.n_refined: List[torch.Tensor] = []      # device counters of the last topk() call
 
-    def _compact(self, item_tab: torch.Tensor, keep_mask: torch.Tensor, key):
-        ck = (item_tab.data_ptr(), item_tab._version, tuple(item_tab.shape), key)
-        hit = self._compact_cache.get(ck)
-        if hit is None:
-            gids = torch.nonzero(keep_mask, as_tuple=False).flatten().to(torch.int32)
-            hit = (ops.gather_rows(item_tab, gids), gids)
-            if len(self._compact_cache) >= 4:        # tables change every epoch: keep the cache tiny
-                self._compact_cache.clear()
-            self._compact_cache[ck] = hit
-        return hit
+    def _kept_ids(self, item_flags: torch.Tensor, keep_mask_fn, key) -> torch.Tensor:
+        """Ids of the items kept by a flag selection.  Only this id list is cached (a function of the flag bytes alone);
+        table rows are gathered afresh on EVERY call and never cached: trainers rebind ``item_emb`` to a new tensor every
+        epoch and the caching allocator hands the same address (and ``_version`` 0) back two epochs later, so any
+        (address, version) key would silently return an old epoch's rows."""
+        ck = (item_flags.data_ptr(), item_flags._version, item_flags.numel(), key)
+        hit = self._gid_cache.get(ck)
+        if hit is None or hit[0] is not item_flags:  # the cached entry keeps the flag tensor alive: its address cannot be reused
+            gids = torch.nonzero(keep_mask_fn(), as_tuple=False).flatten().to(torch.int32)
+            if len(self._gid_cache) >= 16:
+                self._gid_cache.clear()
+            hit = (item_flags, gids)
+            self._gid_cache[ck] = hit
+        return hit[1]
 
     def topk(self, tables, plan: EvalPlan, item_flags: Optional[torch.Tensor] = None):
         K, excl = self.K, plan.flag_exclude
@@ -138,18 +154,17 @@ class FullRankScorer:
             if group is not None:
                 if item_flags is None:
                     raise ValueError("item groups need item_flags")
-                keep = (item_flags & (FLAG_WARM | FLAG_COLD)) == 0 if group == GROUP_UNFLAGGED else (item_flags & group) != 0
-                if excl:
-                    keep = keep & ((item_flags & excl) == 0)
-                tab, gids = self._compact(item_tab, keep, (group, excl))
-                compacted = True
+                def keep(group=group):
+                    k = (item_flags & (FLAG_WARM | FLAG_COLD)) == 0 if group == GROUP_UNFLAGGED else (item_flags & group) != 0
+                    return k & ((item_flags & excl) == 0) if excl else k
+                gids = self._kept_ids(item_flags, keep, (group, excl))
+                tab, compacted = ops.gather_rows(item_tab, gids), True
             elif excl:
-                keep = (item_flags & excl) == 0
-                if int(keep.sum()) < 0.9 * item_tab.shape[0]:      # skipping flagged items outright is cheaper
-                    tab, gids = self._compact(item_tab, keep, (0, excl))
-                    compacted = True
-                else:
-                    kflags, kexcl = item_flags, excl
+                gids = self._kept_ids(item_flags, lambda: (item_flags & excl) == 0, (0, excl))
+                if gids.numel() < 0.9 * item_tab.shape[0]:         # skipping flagged items outright is cheaper
+                    tab, compacted = ops.gather_rows(item_tab, gids), True
+                else:                                              # few items flagged: mask them inside the kernel instead
+                    gids, kflags, kexcl = None, item_flags, excl
             if tab.shape[0] == 0:
                 continue
             s, i, nref = ops.score_topk(user_tab, tab, K, user_ids=plan.user_ids, item_gids=gids, mask_rowptr=plan.mask_rowptr,

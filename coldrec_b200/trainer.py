@@ -86,33 +86,94 @@ class FusedEvalMixin:
     def _ranking_evaluation(self, gt, rec_list, topN):
         return ranking_evaluation(gt, rec_list, topN, item_map=self.data.item, device=self._fused_state()["device"])
 
+    # ---- the consumers of the hot path (reference :230-351).  They are overridden here, not only in the base class below,
+    # because the reference's own versions call the module-level ``util.evaluator.ranking_evaluation`` (:7), which would
+    # materialise every RecList into Python dicts and run the 24 us/user metric loops on the host again. -------------------
+    _SPLIT_NAMES = {'warm': 'warm', 'cold': 'cold', 'all': 'overall'}
+
+    def _split(self, prefix: str, kind: str, what: str):
+        if kind not in self._SPLIT_NAMES:
+            raise ValueError(f'Invalid {what} type!')
+        return getattr(self.data, f'{self._SPLIT_NAMES[kind]}_{prefix}_set')
+
+    def full_evaluation(self, rec_list, test_type: str = 'warm') -> None:
+        """Reference :230-254: metrics at every cut-off of ``topN`` on the test split, kept in ``<setting>_test_results``."""
+        test_set = self._split('test', test_type, 'evaluation')
+        self.result, performance = self._ranking_evaluation(test_set, rec_list, self.topN)
+        setattr(self, self._SPLIT_NAMES[test_type] + '_test_results', performance)
+        print('*' * 80)
+        print(f'[{test_type} setting] The result of %s:\n%s' % (self.model_name, ''.join(self.result)))
+
+    @staticmethod
+    def _metrics_dict_from_measure(measure: List[str]) -> Dict[str, float]:
+        """'NDCG:0.123\n' lines -> {'NDCG': 0.123} (reference :256-262; the format ``ranking_evaluation`` must keep)."""
+        return {k: float(v) for k, v in (m.strip().split(':') for m in measure[1:])}
+
+    @staticmethod
+    def _metrics_all_finite(performance: Dict[str, float]) -> bool:
+        return all(math.isfinite(v) for v in performance.values())
+
+    def _track_best(self, epoch: int, performance: Dict[str, float]) -> None:
+        """Early-stopping state machine of reference :291-327.  A validation counts as an improvement iff its metrics are
+        finite and NDCG@max(topN) is strictly above the best so far (any finite validation, when there is no best yet);
+        an improvement saves the model and — only when a best already existed — refills the patience; anything else costs
+        one unit of patience."""
+        had_best = len(self.bestPerformance) > 0
+        finite = self._metrics_all_finite(performance)
+        if finite and (not had_best or performance['NDCG'] > self.bestPerformance[1]['NDCG']):
+            self.bestPerformance = [epoch + 1, performance]
+            self.save()
+            if had_best and self.early_stop_flag:
+                self.early_stop_patience = self.max_early_stop_patience
+            return
+        if self.early_stop_flag:
+            self.early_stop_patience -= 1
+        if not finite and had_best:
+            print('Warning: validation metrics are non-finite; early-stop patience decreased, best checkpoint unchanged.')
+        elif not finite and self.early_stop_flag:
+            print('Warning: first validation has non-finite metrics; best checkpoint not initialized yet.')
+
+    def fast_evaluation(self, epoch: int, valid_type: str = 'all') -> List[str]:
+        """Reference :268-351: validate at max(topN), update the early-stopping state, print the progress block."""
+        valid_set = self._split('valid', valid_type, 'evaluation')
+        print(f'Evaluating the model under the {valid_type} setting...')
+        measure, _ = self._ranking_evaluation(valid_set, self.valid(valid_type), [self.max_N])
+        self._track_best(epoch, self._metrics_dict_from_measure(measure))
+        lines = [m.strip() for m in measure[1:]]
+        rule = '-' * 120
+        print(rule)
+        print('Performance ' + ' (Top-' + str(self.max_N) + ' Recommendation)')
+        print('*Current Performance*')
+        print('Epoch:', str(epoch + 1) + ',', '  |  '.join(lines))
+        if self.bestPerformance:
+            best_epoch, best = self.bestPerformance
+            print(f'*Best {valid_type} Performance* ')
+            print('Epoch:', str(best_epoch) + ',', '  |  '.join(f'{k}:{best[k]}' for k in ('Hit Ratio', 'Precision', 'Recall', 'NDCG')))
+        else:
+            print(f'*Best {valid_type} Performance* not initialized (waiting for finite validation).')
+        if self.early_stop_flag:
+            print(f"Stopping early at epoch {epoch + 1}." if self.early_stop_patience <= 0
+                  else f"Early stopping patience left: {self.early_stop_patience}.")
+        print(rule)
+        return lines
+
 
 class BaseColdStartTrainer(FusedEvalMixin, ABC):
     """Mirror of model/BaseRecommender.py:13-370 (same constructor contract: ``config.args``,
-    ``config.data``, ``config.device``)."""
+    ``config.data``, ``config.device``) for trainers that do not inherit the reference's class."""
 
     def __init__(self, config):
-        self.config = config
-        self.args = config.args
-        self.data = config.data
-        self.bestPerformance = []
-        self.topN = [int(num) for num in self.args.topN.split(',')]
+        self.config, self.args, self.data, self.device = config, config.args, config.data, config.device
+        a = self.args
+        self.model_name, self.dataset_name, self.emb_size = a.model, a.dataset, a.emb_size
+        self.maxEpoch, self.batch_size, self.lr, self.reg = a.epochs, a.bs, a.lr, a.reg
+        self.topN = [int(n) for n in a.topN.split(',')]
         self.max_N = max(self.topN)
-        self.model_name = self.args.model
-        self.dataset_name = self.args.dataset
-        self.emb_size = self.args.emb_size
-        self.maxEpoch = self.args.epochs
-        self.batch_size = self.args.bs
-        self.lr = self.args.lr
-        self.reg = self.args.reg
-        self.device = self.config.device
-        self.result = []
-        self.early_stop_flag = self.args.early_stop != 0
+        self.bestPerformance, self.result, self.epochs_ran = [], [], 0
+        self.early_stop_flag = a.early_stop != 0
         if self.early_stop_flag:
-            self.early_stop_patience = self.args.early_stop
-            self.max_early_stop_patience = self.args.early_stop
-        self.epochs_ran = 0
-        self.eval_every = max(1, int(getattr(self.args, 'eval_every', 1)))
+            self.early_stop_patience = self.max_early_stop_patience = a.early_stop
+        self.eval_every = max(1, int(getattr(a, 'eval_every', 1)))
 
     def print_basic_info(self):
         print('*' * 80)
@@ -122,10 +183,7 @@ class BaseColdStartTrainer(FusedEvalMixin, ABC):
         print('*' * 80)
 
     def timer(self, start=True):
-        if start:
-            self.train_start_time = time.time()
-        else:
-            self.train_end_time = time.time()
+        setattr(self, 'train_start_time' if start else 'train_end_time', time.time())
 
     @abstractmethod
     def train(self) -> None: ...
@@ -146,81 +204,11 @@ class BaseColdStartTrainer(FusedEvalMixin, ABC):
             uids = torch.as_tensor(self.data.get_user_id_list(users), device=self.get_user_emb().device)
             return torch.matmul(self.get_user_emb()[uids], self.get_item_emb().transpose(0, 1))
 
-    def _set(self, prefix: str, kind: str):
-        name = {'warm': 'warm', 'cold': 'cold', 'all': 'overall'}.get(kind)
-        if name is None:
-            raise ValueError(f'Invalid {prefix} type!')
-        return getattr(self.data, f'{name}_{prefix}_set')
-
     def valid(self, valid_type: str = 'all'):
-        return self._evaluate(self._set('valid', valid_type), valid_type)
+        return self._evaluate(self._split('valid', valid_type, 'valid'), valid_type)
 
     def test(self, test_type: str = 'all'):
-        return self._evaluate(self._set('test', test_type), test_type)
-
-    def full_evaluation(self, rec_list, test_type: str = 'warm') -> None:
-        test_set = self._set('test', test_type)
-        self.result, test_performance = self._ranking_evaluation(test_set, rec_list, self.topN)
-        setattr(self, {'warm': 'warm', 'cold': 'cold', 'all': 'overall'}[test_type] + '_test_results', test_performance)
-        print('*' * 80)
-        print(f'[{test_type} setting] The result of %s:\n%s' % (self.model_name, ''.join(self.result)))
-
-    @staticmethod
-    def _metrics_dict_from_measure(measure: List[str]) -> Dict[str, float]:
-        out = {}
-        for m in measure[1:]:
-            k, v = m.strip().split(':')
-            out[k] = float(v)
-        return out
-
-    @staticmethod
-    def _metrics_all_finite(performance: Dict[str, float]) -> bool:
-        return all(math.isfinite(v) for v in performance.values())
-
-    def fast_evaluation(self, epoch: int, valid_type: str = 'all') -> List[str]:
-        """Reference :268-351: validate at max(topN); strict NDCG improvement saves and resets patience."""
-        valid_set = self._set('valid', valid_type)
-        print(f'Evaluating the model under the {valid_type} setting...')
-        rec_list = self.valid(valid_type)
-        measure, _ = self._ranking_evaluation(valid_set, rec_list, [self.max_N])
-        performance = self._metrics_dict_from_measure(measure)
-        finite = self._metrics_all_finite(performance)
-        if self.bestPerformance:
-            if finite and performance['NDCG'] > self.bestPerformance[1]['NDCG']:      # strict improvement, :306-316
-                self.bestPerformance = [epoch + 1, performance]
-                self.save()
-                if self.early_stop_flag:
-                    self.early_stop_patience = self.max_early_stop_patience
-            else:
-                if self.early_stop_flag:
-                    self.early_stop_patience -= 1
-                if not finite:
-                    print('Warning: validation metrics are non-finite; early-stop patience decreased, best checkpoint unchanged.')
-        elif finite:                                                                  # :318-321
-            self.bestPerformance = [epoch + 1, performance]
-            self.save()
-        elif self.early_stop_flag:                                                    # :322-327
-            self.early_stop_patience -= 1
-            print('Warning: first validation has non-finite metrics; best checkpoint not initialized yet.')
-
-        print('-' * 120)
-        print('Performance ' + ' (Top-' + str(self.max_N) + ' Recommendation)')
-        measure_lines = [m.strip() for m in measure[1:]]
-        print('*Current Performance*')
-        print('Epoch:', str(epoch + 1) + ',', '  |  '.join(measure_lines))
-        if self.bestPerformance:
-            bp = '  |  '.join(k + ':' + str(self.bestPerformance[1][k]) for k in ('Hit Ratio', 'Precision', 'Recall', 'NDCG'))
-            print(f'*Best {valid_type} Performance* ')
-            print('Epoch:', str(self.bestPerformance[0]) + ',', bp)
-        else:
-            print(f'*Best {valid_type} Performance* not initialized (waiting for finite validation).')
-        if self.early_stop_flag:
-            if self.early_stop_patience <= 0:
-                print(f"Stopping early at epoch {epoch + 1}.")
-            else:
-                print(f"Early stopping patience left: {self.early_stop_patience}.")
-        print('-' * 120)
-        return measure_lines
+        return self._evaluate(self._split('test', test_type, 'test'), test_type)
 
     def run(self) -> None:
         """Reference :353-370: train, then test + evaluate under all / cold / warm."""
@@ -229,12 +217,12 @@ class BaseColdStartTrainer(FusedEvalMixin, ABC):
         self.train()
         if getattr(self, 'epochs_ran', 0) == 0 and self.maxEpoch > 0:
             self.epochs_ran = self.maxEpoch
-        for test_type in ['all', 'cold', 'warm']:
+        for setting in ('all', 'cold', 'warm'):
             print('*' * 80)
-            print(f'Testing under [{test_type}] setting...')
-            rec_list = self.test(test_type=test_type)
-            print(f'Evaluating under [{test_type}] setting...')
-            self.full_evaluation(rec_list, test_type=test_type)
+            print(f'Testing under [{setting}] setting...')
+            rec_list = self.test(test_type=setting)
+            print(f'Evaluating under [{setting}] setting...')
+            self.full_evaluation(rec_list, test_type=setting)
 
 
 class AldiScoreTables:

@@ -91,7 +91,7 @@ def test_train_csr_flags_sets_and_errors():
     uid_sets = got.training_set_uid
     for u, uid in ref.user.items():
         assert uid_sets[uid] == set(ref.training_set_u[u]) if u in ref.training_set_u else uid_sets[uid] == set()
-    assert got.training_size() == (len(ref.training_set_u), len(ref.training_set_i), len(args[0]))
+    assert got.training_size() == (len(ref.user), len(ref.item), len(args[0]))      # util/databuilder.py:307-308
     with pytest.raises(Exception, match="user 99999 not in current id table"):
         got.get_user_id(99999)
     with pytest.raises(Exception, match="item 12345 not in current id table"):

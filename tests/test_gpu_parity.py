@@ -234,6 +234,39 @@ def test_aldi_dual_tables_vs_reference_golden(typ, precision):
                         _exact_scores_fn(data, score_rows, users, typ, "item"))
 
 
+def test_reevaluation_after_item_table_is_freed_and_reallocated():
+    """trainers rebind ``item_emb`` to a fresh tensor every epoch and the caching allocator hands the
+    same address (version 0) back two epochs later; a compaction cache keyed on (address, version) then returned an old
+    epoch's rows.  Evaluate ALDI-style (three compacted item groups) over six epochs of freed-and-reallocated tables with
+    different contents and compare every epoch with the oracle."""
+    from coldrec_b200 import AldiScoreTables
+    g = load_golden("eval_item")
+    data = O.OracleData(*builder_args(g))
+    tr = _trainer(data, "item", PRECISIONS[1], base=AldiScoreTables)
+    rng = np.random.default_rng(5)
+    seen_ptrs = set()
+    for epoch in range(6):
+        I = (rng.standard_normal(g["item_emb"].shape) * 0.1).astype(np.float32)
+        Uw = (rng.standard_normal(g["user_emb"].shape) * 0.1).astype(np.float32)
+        Uc = (rng.standard_normal(g["user_emb"].shape) * 0.1).astype(np.float32)
+        tr.item_emb = None                                   # free last epoch's block first, like a rebinding trainer
+        tr.item_emb = cu(I).clone()
+        tr.warm_user_emb, tr.cold_user_emb = cu(Uw), cu(Uc)
+        seen_ptrs.add(tr.item_emb.data_ptr())
+        for typ in ("cold", "warm"):
+            rec = tr.test(typ)
+            users = list(getattr(data, f"{typ}_test_set").keys())
+            uid = data.get_user_id_list(users)
+            fn = O.score_aldi(t(Uw), t(Uc), t(I), data.mapped_warm_item_idx, data.mapped_cold_item_idx)
+            score_rows = lambda j: fn(torch.tensor([uid[j]]))[0].numpy()
+            exact = _exact_scores_fn(data, score_rows, users, typ, "item")
+            got_s, got_i = rec.scores.cpu().numpy(), rec.ids.cpu().numpy().astype(np.int64)
+            for j in range(len(users)):
+                want = np.asarray(exact(j, got_i[j]), dtype=np.float32)
+                assert np.allclose(got_s[j], want, atol=1e-5), f"epoch {epoch} {typ} user {j}: scores are not this epoch's"
+    assert len(seen_ptrs) < 6, "the allocator never reused an address: the scenario was not exercised"
+
+
 @pytest.mark.parametrize("precision", PRECISIONS, ids=["exact", "tf32"])
 def test_vbpr_two_products_vs_reference_golden(precision):
     from coldrec_b200 import TwoProductScoreTables
