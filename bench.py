@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--graph-edges", type=int, default=GRAPH_EDGES)
     ap.add_argument("--cpu-sample-users", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default="C1,C2,C3", help="dataset-shaped side lines under \"extra\" (N=1 only): any of C1,C2,C3")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C2 / C3 dataset-shaped lines")
+    ap.add_argument("--config-steps", type=int, default=5)
     ap.add_argument("--shard", default="auto", choices=["auto", "items", "users"],
                     help="N>1 scoring layout.  items: the catalogue split N ways + NCCL candidate all-gather (north star).  auto "
                          "(default): the same, but item shards are kept at >= --min-shard-items items; beyond that the ranks form "
@@ -58,6 +61,9 @@ def parse():
                          "with their owner (what item-sharded scoring consumes)")
     ap.add_argument("--multicast", action="store_true",
                     help="multi-GPU propagation: rows wanted by every GPU leave as one NVLS multimem.st (measured slower; default unicast)")
+    ap.add_argument("--peer-store", default="tma", choices=["tma", "st"],
+                    help="multi-GPU propagation: how finished rows reach the peers — staged in shared memory and pushed by TMA bulk "
+                         "copies (default), or one 16-byte st.global per lane and destination (round-1 path, kept for A/B)")
     ap.add_argument("--dense-exchange", action="store_true", help="multi-GPU propagation: send every row to every GPU (no need masks)")
     ap.add_argument("--no-train", action="store_true", help="skip the LightGCN training-step line of the lightgcn workload")
     ap.add_argument("--train-batch", type=int, default=4096)
@@ -284,6 +290,8 @@ def run_b200(args):
                    gpu_launches=int(launches), roofline=roofline, clocks=clk.summary(),
                    check={"ndcg@20": perf[1][3], "recall@20": perf[1][2],
                           "n_refined_last_step": int(scorer.last_n_refined.item()) if scorer.last_n_refined is not None else None})
+        if world > 1:
+            out["check"].update(check_sharded_ids(args, scorer, user_tab, item_shard, ib, plans[-1], S, device, world))
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_score_baseline(user_tab, item_shard, plans_d[W], args.cpu_sample_users)
             out["gpu_library_baseline"] = library_score_baseline(user_tab, item_shard, plans_d[W])
@@ -296,6 +304,17 @@ def run_b200(args):
             out = lg
         else:
             out["lightgcn"] = lg
+    if world == 1 and not args.no_configs:
+        import bench_configs
+        torch.cuda.empty_cache()
+        out["extra"] = {}
+        for key in [k for k in args.configs.split(",") if k in bench_configs.CONFIGS]:
+            try:
+                out["extra"][key] = bench_configs.run_config(key, device, lib, steps=args.config_steps, warmup=2,
+                                                             cpu=not args.no_cpu_baseline, host_threads=host_threads())
+            except Exception as ex:      # a dataset-shaped side line must never cost the headline line
+                out["extra"][key] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+            torch.cuda.empty_cache()
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -343,7 +362,11 @@ def run_lightgcn(args, device, rank, world, pk, pk_src, lib):
                                  segments=(n_users, n_items))
         PG.local.plan(D)
         E0 = torch.cat([E0u, E0i])
-        exchange = "SpMM epilogue peer stores over NVLink (fused all-gather)"
+        if args.peer_store == "st":
+            os.environ["CR_SPMM_PEER_ST"] = "1"
+        exchange = ("SpMM epilogue -> shared-memory staging -> TMA bulk stores (cp.async.bulk) into the readers' tables over NVLink "
+                    "(fused all-gather)" if args.peer_store == "tma" and not args.multicast else
+                    "SpMM epilogue 16-byte peer stores over NVLink (fused all-gather)")
         try:
             PG.enable_p2p(D)
             rep = None if args.prop_result == "full" else (0,)
@@ -405,6 +428,9 @@ def run_lightgcn(args, device, rank, world, pk, pk_src, lib):
                          "rows_kernel_ms": round(rows_ms, 3), "rows_kernel_launches": cnt.value,
                          "share_of_step": round(tot.value / ms, 4)},
                clocks=clk.summary())
+    if world > 1:
+        out["check"] = check_partitioned_propagation(G, E0u, E0i, res, PG, args, device, world)
+        out["nvlink"] = nvlink_bytes(PG, args, ms / Ksteps, device, world)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_spmm_baseline(G, E0u, E0i)
         out["gpu_library_baseline"] = library_spmm_baseline(G, E0u, E0i)
@@ -454,6 +480,84 @@ def run_train_step(args, device, G, E0u, E0i, pk, lib):
                          "frac": round(step_bytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4), "bytes_per_step": step_bytes},
             "loss": [round(x, 6) for x in loss.cpu().tolist()[:3]], "sampler_exhausted": int(smp.n_exhausted.item())}
 
+
+
+# ------------------------------------------------------------------------------------------- multi-GPU result checks
+def check_sharded_ids(args, scorer, user_tab, item_shard, ib, plan, S, device, world, n_sample=4096):
+    """N>1: the merged lists this rank holds for the first `n_sample` users of its slice must equal, bit for bit, ONE
+    un-sharded sweep of the same users over the whole catalogue (rebuilt here from the shard seeds) — ids and scores."""
+    import torch.distributed as dist
+    from coldrec_b200 import ops
+    from coldrec_b200.dist import shard_range
+    s, i = scorer.topk(user_tab, item_shard, ib, plan)
+    lo, hi = scorer.user_slice(plan.n_q)
+    n = min(n_sample, hi - lo)
+    parts = []
+    for sh in range(S):      # the whole catalogue, shard by shard, from the generators the ranks used
+        b, e = shard_range(args.n_items, sh, S)
+        parts.append(torch.randn(e - b, D, device=device, generator=torch.Generator(device=device).manual_seed(1000 + sh)) * 0.125)
+    full = torch.cat(parts) if len(parts) > 1 else parts[0]
+    del parts
+    sub = plan.slice(lo, lo + n)
+    rs, ri, _ = ops.score_topk(user_tab, full, K, user_ids=sub.user_ids, mask_rowptr=sub.mask_rowptr, mask_col=sub.mask_col,
+                               precision=ops.SCORE_TF32_CHECKED)
+    ok = torch.tensor([int(torch.equal(ri, i[:n])), int(torch.equal(rs, s[:n]))], device=device)
+    del full
+    torch.cuda.empty_cache()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    return {"ids_equal": bool(ok[0].item()), "scores_equal": bool(ok[1].item()), "ids_checked_users_per_rank": n,
+            "ids_checked_against": f"one un-sharded sweep over all {args.n_items} items on every rank"}
+
+
+def check_partitioned_propagation(G, E0u, E0i, res, PG, args, device, world):
+    """N>1: every row this rank holds of the partitioned result vs a single-GPU propagation of the same graph run on
+    this rank (every rank has the whole graph): norm-wise error max|d| / max|ref|, max over ranks."""
+    import coldrec_b200 as cr
+    import torch.distributed as dist
+    n_users = E0u.shape[0]
+    ru, ri = cr.propagate(G, E0u, E0i, LAYERS)
+    scale = max(ru.abs().max().item(), ri.abs().max().item())
+    if args.prop_result == "full":
+        err = max((res[:n_users] - ru).abs().max().item(), (res[n_users:] - ri).abs().max().item())
+        rows = res.shape[0]
+    else:                    # user rows everywhere, item rows with their owner
+        (ub, ue), (ib_, ie_) = PG.parts[PG.rank]
+        err = max((res[:n_users] - ru).abs().max().item(), (res[ib_:ie_] - ri[ib_ - n_users:ie_ - n_users]).abs().max().item())
+        rows = n_users + (ie_ - ib_)
+    deg = G.rowptr[1:] - G.rowptr[:-1]
+    t_ = torch.tensor([err / scale], dtype=torch.float64, device=device)
+    dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+    del ru, ri
+    torch.cuda.empty_cache()
+    return {"prop_rel_err": float(t_.item()), "rows_checked_per_rank": int(rows), "longest_row_nnz": int(deg.max().item()),
+            "against": "single-GPU cr.propagate of the same graph on every rank (all rows, incl. the long-row split path)",
+            "tolerance": 1e-5}
+
+
+def nvlink_bytes(PG, args, ms_step, device, world):
+    """Bytes this step's fused all-gather moves over NVLink, from the need masks (exact: one d*4-byte row per remote reader
+    and layer), and the per-GPU egress rate they imply; 770 GB/s per direction is the measured peer-copy rate
+    (B200_PROFILING.md)."""
+    import torch.distributed as dist
+    self_bit = 1 << PG.rank
+    def remote_copies(need):
+        if need is None:
+            return PG.n_local * (world - 1)
+        m = need[:PG.n_local].to(torch.int32) & ~self_bit
+        return int(sum(((m >> p) & 1).sum().item() for p in range(world)))
+    inner = remote_copies(None if args.dense_exchange else PG._need)
+    if args.prop_result == "full":
+        last = PG.n_local * (world - 1)
+    else:
+        last = remote_copies(PG._need_last.get((0,)))
+    egress = (inner * (LAYERS - 1) + last) * D * 4
+    t_ = torch.tensor([egress], dtype=torch.float64, device=device)
+    tmax = t_.clone()
+    dist.all_reduce(t_, op=dist.ReduceOp.SUM)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    return {"bytes_per_step_all_gpus": int(t_.item()), "egress_bytes_per_step_max_gpu": int(tmax.item()),
+            "egress_gbs_max_gpu": round(tmax.item() / (ms_step * 1e-3) / 1e9, 1), "peer_copy_peak_gbs": 770.0,
+            "nvlink_bound_ms": round(tmax.item() / 770e9 * 1e3, 3)}
 
 # ------------------------------------------------------------------------------------------- the reference's GPU path
 def _event_ms(fn, iters=3, warm=1):
@@ -549,23 +653,83 @@ def cpu_spmm_baseline(G, E0u, E0i, frac=0.05):
             "sample": f"one layer over the first {n_rows} rows ({hi - lo} nonzeros, {frac:.0%} of rows) of the C4 adjacency, {dt:.1f} s"}
 
 
+class _CatalogueData:
+    """What ``BaseColdStartTrainer._evaluate`` / ``_get_eval_cache`` / ``MF.batch_predict`` touch of a data builder
+    (model/BaseRecommender.py:109-188, model/MF.py:58-63), for a catalogue too large for the reference's dict builders:
+    raw ids ARE dense ids, train items only for the sampled users."""
+
+    def __init__(self, n_users, n_items, plan):
+        from collections import defaultdict
+        self.user_num, self.item_num = n_users, n_items
+        self.id2item = range(n_items)
+        self.training_set_u = defaultdict(dict)
+        uids, rp, col = plan["user_ids"].tolist(), plan["mask_rowptr"].tolist(), plan["mask_col"].tolist()
+        grp, gcol = plan["gt_rowptr"].tolist(), plan["gt_col"].tolist()
+        self.overall_test_set = {}
+        for j, u in enumerate(uids):
+            self.training_set_u[u] = dict.fromkeys(col[rp[j]:rp[j + 1]], 1.0)
+            self.overall_test_set[u] = dict.fromkeys(gcol[grp[j]:grp[j + 1]], 1.0)
+        self.mapped_cold_item_idx = self.mapped_warm_item_idx = []
+
+    def get_user_id_list(self, users):
+        return np.asarray(users)
+
+    def get_item_id_list(self, items):
+        return np.asarray(items)
+
+
+def reference_step_factory(args, U, I):
+    """One step of the reference arm.  With baseline/_ref present (it travels with the snapshot): the reference's OWN
+    ``MF.batch_predict`` + ``BaseColdStartTrainer._evaluate`` + ``util.evaluator.ranking_evaluation``, unmodified, with the
+    eval batch (``--bs``) = the sampled users: a (sample x 10M) fp32 score matrix, 5 GB at 128 users — the literal code
+    path, which is why the sample is small.  Otherwise the oracle port (item-chunked restatement)."""
+    import types
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import refimport
+    finally:
+        sys.path.pop(0)
+    n_q = args.cpu_sample_users
+    if refimport.available():
+        refimport.import_reference()
+        from model.BaseRecommender import BaseColdStartTrainer
+        from model.MF import MF
+        from util.evaluator import ranking_evaluation
+
+        def step(p):
+            data = _CatalogueData(args.n_users, args.n_items, p)
+            ns = types.SimpleNamespace(topN="10,20", model="MF", dataset="syn", emb_size=D, epochs=0, bs=n_q, lr=1e-3, reg=1e-4,
+                                       early_stop=0, eval_every=1, cold_object="item", save_emb=False)
+            tr = object.__new__(MF)          # MF.__init__ would allocate (and xavier-initialise) a second 10M x 64 table
+            BaseColdStartTrainer.__init__(tr, types.SimpleNamespace(args=ns, data=data, device=torch.device("cpu")))
+            tr.user_emb, tr.item_emb = U, I
+            rec = tr.test("all")
+            measure, perf = ranking_evaluation(data.overall_test_set, rec, TOPN)
+            return perf
+        return step, "reference", (f"{n_q} users/step x {args.n_items} items: the reference's own MF.batch_predict + _evaluate (one "
+                                   f"{n_q}-user batch) + ranking_evaluation from baseline/_ref")
+    from oracle import coldrec_oracle as O
+
+    def step(p):
+        s, i = O.evaluate_topk_dense_chunked(U, I, p["user_ids"].numpy(), p["mask_rowptr"].numpy(), p["mask_col"].numpy().astype(np.int64),
+                                             None, K, user_batch=min(128, n_q), item_chunk=1 << 20)
+        return O.metrics_from_topk(i, p["gt_rowptr"].numpy(), p["gt_col"].numpy().astype(np.int64), TOPN)
+    return step, "port", f"{n_q} users/step x {args.n_items} items, item-chunked torch CPU matmul + mask + topk + metrics (oracle port)"
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port: torch CPU matmul /
-    topk / sparse.mm exactly as ColdRec calls them), all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, all host threads, a bounded
+    sample per step (see reference_step_factory)."""
     rank, _, world = dist_env()
     if rank != 0:
         return
-    from oracle import coldrec_oracle as O
     torch.set_num_threads(host_threads())
     n_q = args.cpu_sample_users
     g = torch.Generator().manual_seed(1)
     U = torch.randn(args.n_users, D, generator=g) * 0.125
     I = torch.randn(args.n_items, D, generator=g) * 0.125
     plans = make_step_plans(args.warmup + args.steps, n_q, args.n_users, args.n_items, 6, torch.device("cpu"))
-    def step(p):
-        s, i = O.evaluate_topk_dense_chunked(U, I, p["user_ids"].numpy(), p["mask_rowptr"].numpy(), p["mask_col"].numpy().astype(np.int64),
-                                             None, K, user_batch=min(128, n_q), item_chunk=1 << 20)
-        return O.metrics_from_topk(i, p["gt_rowptr"].numpy(), p["gt_col"].numpy().astype(np.int64), TOPN)
+    step, kind, sample = reference_step_factory(args, U, I)
     for p in plans[:args.warmup]:
         step(p)
     t0 = time.perf_counter()
@@ -574,16 +738,24 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = n_q * args.steps / dt
     cores = torch.get_num_threads()
-    sample = f"{n_q} users/step x {args.n_items} items, item-chunked torch CPU matmul + mask + topk + metrics"
-    print(json.dumps(dict(impl="reference", metric="full-rank users/sec (top-20 over catalog)", value=round(value, 2), unit="users/s",
-                          n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=round(dt / args.steps * 1e3, 1),
-                          higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                          config={"workload": score_workload(args, args.users_per_step * world), "parallelism": "host cores (CPU reference path)",
-                                  "users_per_step": args.users_per_step * world, "n_items": args.n_items, "K": K,
-                                  "sampled_users_per_step": n_q},
-                          cpu_baseline={"value": round(value, 2), "unit": "users/s", "cores": cores, "kind": "port", "sample": sample},
-                          e2e={"value": round(value, 2), "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          gpu_launches=0, check={"ndcg@20": perf[1][3]})), flush=True)
+    line = dict(impl="reference", metric="full-rank users/sec (top-20 over catalog)", value=round(value, 2), unit="users/s",
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=round(dt / args.steps * 1e3, 1),
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config={"workload": score_workload(args, args.users_per_step * world), "parallelism": "host cores (CPU reference path)",
+                        "users_per_step": args.users_per_step * world, "n_items": args.n_items, "K": K,
+                        "sampled_users_per_step": n_q},
+                cpu_baseline={"value": round(value, 2), "unit": "users/s", "cores": cores, "kind": kind, "sample": sample},
+                e2e={"value": round(value, 2), "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                gpu_launches=0, check={"ndcg@20": perf[1][3]})
+    if not args.no_configs and world == 1:
+        import bench_configs
+        line["extra"] = {}
+        for key in [k for k in args.configs.split(",") if k in bench_configs.CONFIGS]:
+            try:
+                line["extra"][key] = bench_configs.reference_config_line(key, cores)
+            except Exception as ex:
+                line["extra"][key] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -10,6 +10,8 @@
 // so a warp keeps U*(32/LPR) row gathers (2 KB at d=64) outstanding.  Rows longer than kLongRow are
 // cut into kChunk-nonzero chunks (one warp each, partial sums in the plan buffer) and reduced in
 // chunk order by a third kernel, so results do not depend on scheduling.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -172,33 +174,83 @@ __device__ __forceinline__ int64_t peer_index(const Epi& ep, int64_t idx) {
     return idx + (idx < ep.peer_split4 ? ep.peer_off4 : ep.peer_off_hi4);
 }
 
-// y -> Y and/or acc = (beta*acc_in + y) / div for one float4 of one row (acc_in may alias acc).
-__device__ __forceinline__ void store_epilogue(const Epi& ep, int64_t row, int64_t idx, float4 y) {
+// Local part of the epilogue (Y / running layer sum) for one float4; returns the value the peers receive.
+__device__ __forceinline__ float4 epilogue_local(const Epi& ep, int64_t idx, float4 y) {
     if (ep.Y4) ep.Y4[idx] = y;
-    unsigned need = 0xffffffffu;
-    if (ep.peers && ep.peer_need) need = __ldg(ep.peer_need + row);
-    if (ep.peers && !ep.peers_get_acc) {
-        store_peers(ep, need, peer_index(ep, idx), y);
+    if (!ep.acc4) return y;
+    float4 o = y;
+    if (ep.beta != 0.f) {
+        const float4 q = ep.acc_in4[idx];
+        o.x = fmaf(ep.beta, q.x, y.x);
+        o.y = fmaf(ep.beta, q.y, y.y);
+        o.z = fmaf(ep.beta, q.z, y.z);
+        o.w = fmaf(ep.beta, q.w, y.w);
     }
-    if (ep.acc4) {
-        float4 o = y;
-        if (ep.beta != 0.f) {
-            const float4 q = ep.acc_in4[idx];
-            o.x = fmaf(ep.beta, q.x, y.x);
-            o.y = fmaf(ep.beta, q.y, y.y);
-            o.z = fmaf(ep.beta, q.z, y.z);
-            o.w = fmaf(ep.beta, q.w, y.w);
+    if (ep.div != 1.f) {
+        o.x = __fdiv_rn(o.x, ep.div);
+        o.y = __fdiv_rn(o.y, ep.div);
+        o.z = __fdiv_rn(o.z, ep.div);
+        o.w = __fdiv_rn(o.w, ep.div);
+    }
+    ep.acc4[idx] = o;
+    return ep.peers_get_acc ? o : y;
+}
+
+// y -> Y and/or acc = (beta*acc_in + y) / div for one float4 of one row (acc_in may alias acc), then the SM-issued peer stores.
+__device__ __forceinline__ void store_epilogue(const Epi& ep, int64_t row, int64_t idx, float4 y) {
+    const float4 v = epilogue_local(ep, idx, y);
+    if (ep.peers) {
+        const unsigned need = ep.peer_need ? (unsigned)__ldg(ep.peer_need + row) : 0xffffffffu;
+        store_peers(ep, need, peer_index(ep, idx), v);
+    }
+}
+
+// ---- staged peer stores (multi-GPU): finished rows are parked in shared memory, 8 consecutive rows per half-buffer, and
+// pushed to the peers' gather tables by the TMA engine (cp.async.bulk shared -> peer global over NVLink) in runs of
+// consecutive rows per destination: 256 B for a row only some GPUs read, up to 2 KB where 8 neighbours go to the same
+// GPU (user rows in every layer, every row of the replicated last layer).  The SM-issued variant above (one 16-byte
+// st.global per lane and destination) held the whole SpMM back once 4+ GPUs exchange rows (r01: 8 GPUs slower than 4):
+// the stores sit in the LSU queues in front of the row gathers.  Bulk copies are asynchronous, leave the load path
+// alone and are tracked per issuing thread (bulk groups), so a warp only waits when both of its half-buffers are in flight.
+constexpr int kStageRows = 8;        // rows per half-buffer (two half-buffers per warp)
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// One half-buffer (rows [row0, row0 + 8) of this warp, d4 float4 each) -> every GPU that reads them.  Lane p serves
+// destination p: its bit mask over the 8 rows is cut into runs of consecutive rows (and at the boundary between the two
+// destination ranges), one bulk copy per run.  skip8: rows not produced by this warp (split-path rows, rows past the end).
+__device__ __forceinline__ void flush_stage(const Epi& ep, const float4* half, int64_t row0, int64_t n_rows, unsigned skip8,
+                                            int d4, int lane) {
+    fence_proxy_async_smem();        // this lane's st.shared -> visible to the async proxy (TMA) ...
+    __syncwarp();                    // ... and every lane's before any lane issues a copy
+    if (lane < ep.n_peers) {
+        unsigned m = 0;
+#pragma unroll
+        for (int j = 0; j < kStageRows; ++j) {
+            const int64_t row = row0 + j;
+            if (row < n_rows && !((skip8 >> j) & 1u)) {
+                const unsigned nd = ep.peer_need ? (unsigned)__ldg(ep.peer_need + row) : 0xffffffffu;
+                m |= ((nd >> lane) & 1u) << j;
+            }
         }
-        if (ep.div != 1.f) {
-            o.x = __fdiv_rn(o.x, ep.div);
-            o.y = __fdiv_rn(o.y, ep.div);
-            o.z = __fdiv_rn(o.z, ep.div);
-            o.w = __fdiv_rn(o.w, ep.div);
+        float4* dst = ep.peers[lane];
+        while (m) {
+            const int j0 = __ffs(m) - 1;
+            int len = __ffs(~(m >> j0)) - 1;                        // consecutive rows wanted by this GPU
+            const int64_t idx0 = (row0 + j0) * d4;
+            if (idx0 < ep.peer_split4 && idx0 + (int64_t)len * d4 > ep.peer_split4) len = (int)((ep.peer_split4 - idx0) / d4);
+            bulk_store_s2g(dst + peer_index(ep, idx0), half + j0 * d4, (uint32_t)(len * d4 * sizeof(float4)));
+            m &= ~(((1u << len) - 1u) << j0);
         }
-        ep.acc4[idx] = o;
-        if (ep.peers && ep.peers_get_acc) {
-            store_peers(ep, need, peer_index(ep, idx), o);
-        }
+        bulk_commit();               // exactly one group per flush and lane (empty ones included): wait_group counts flushes
     }
 }
 
@@ -254,7 +306,7 @@ __device__ __noinline__ void walk_chunks(const PlanHeader* __restrict__ hdr, con
 // owns 128 consecutive rows: row pointers are fetched 32 rows at a time, column ids / values of the next batch
 // of rows and of the next chunk of the same row are prefetched while the current gathers are in flight, and
 // 32/LPR rows are gathered concurrently, so the chain is paid once per 32 rows instead of once per row.
-template <int LPR, int NV, bool HAS_VAL, int U, int MINB>
+template <int LPR, int NV, bool HAS_VAL, int U, int MINB, bool STAGED = false>
 __global__ void __launch_bounds__(kThreads, MINB)
 spmm_rows_grouped_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
                          int64_t n_rows, const float4* __restrict__ X4, const Epi ep, int long_row, int kRowsPerWarp,
@@ -264,6 +316,11 @@ spmm_rows_grouped_kernel(const int64_t* __restrict__ rowptr, const int32_t* __re
     constexpr int d4 = LPR * NV;
     static_assert(LPR % U == 0, "a group's LPR column ids are consumed U at a time");
     const int lane = threadIdx.x & 31, grp = lane / LPR, sub = lane % LPR;
+    // STAGED (multi-GPU): two half-buffers of kStageRows rows per warp for the TMA peer stores (see flush_stage)
+    constexpr int kBatchesPerHalf = kStageRows / RPW;
+    static_assert(kStageRows % RPW == 0 && (32 / kStageRows) % 2 == 0, "half-buffers alternate 0,1 inside every 32-row block");
+    __shared__ __align__(128) float4 s_stage[STAGED ? (kThreads / 32) * 2 * kStageRows * d4 : 1];
+    float4* const stage = s_stage + (STAGED ? (threadIdx.x >> 5) * 2 * kStageRows * d4 : 0);
     if ((int)blockIdx.x < chunk_ctas) {
         // The first CTAs of the grid walk the chunks of the long rows (one warp per chunk, partial sums to the plan buffer):
         // the longest work items start first and share the launch — and its tail — with the ordinary rows instead of
@@ -280,6 +337,7 @@ spmm_rows_grouped_kernel(const int64_t* __restrict__ rowptr, const int32_t* __re
         int64_t hi = __ldg(rowptr + min(rr + 1, n_rows));
         const bool skip_row = (rr >= n_rows) || (hi - lo > long_row);   // long rows belong to the split path
         if (skip_row) hi = lo;
+        [[maybe_unused]] const unsigned skip32 = STAGED ? __ballot_sync(CR_FULL_MASK, skip_row) : 0u;
         int c_nb = 0;
         float v_nb = 0.f;
 #pragma unroll 1
@@ -333,11 +391,30 @@ spmm_rows_grouped_kernel(const int64_t* __restrict__ rowptr, const int32_t* __re
                 c = c_nc;
                 v = v_nc;
             }
-            if (!skip && row < n_rows) {
+            if constexpr (STAGED) {
+                const int half = (b / kBatchesPerHalf) & 1, slot = (b % kBatchesPerHalf) * RPW + grp;
+                float4* const hb = stage + half * kStageRows * d4;
+                if (b % kBatchesPerHalf == 0) {      // about to refill this half: its previous copies must have read it
+                    if (lane < ep.n_peers) bulk_wait_read<1>();
+                    __syncwarp();
+                }
+                if (!skip && row < n_rows) {
+#pragma unroll
+                    for (int nv = 0; nv < NV; ++nv)
+                        hb[slot * d4 + sub + nv * LPR] = epilogue_local(ep, row * d4 + sub + nv * LPR, a[nv]);
+                }
+                if (b % kBatchesPerHalf == kBatchesPerHalf - 1) {
+                    const int r8 = (b / kBatchesPerHalf) * kStageRows;
+                    flush_stage(ep, hb, r32 + r8, n_rows, (skip32 >> r8) & 0xffu, d4, lane);
+                }
+            } else if (!skip && row < n_rows) {
 #pragma unroll
                 for (int nv = 0; nv < NV; ++nv) store_epilogue(ep, row, row * d4 + sub + nv * LPR, a[nv]);
             }
         }
+    }
+    if constexpr (STAGED) {
+        if (lane < ep.n_peers) bulk_wait_all();      // the copies must have landed before the CTA (and its smem) goes away
     }
 }
 
@@ -444,7 +521,7 @@ int launch_spmm(const SpmmArgs& a) {
         if (a.n_rows > 0) {
             // 128 rows per warp amortise the row-pointer fetches on big graphs; dataset-sized graphs (10^4 .. 10^5 rows) get 32
             // rows per warp so that the grid still covers the SMs (CiteULike-shaped, 22.5k rows: 22 -> 88 CTAs)
-            const bool big = a.n_rows >= (int64_t)148 * 24 * 128;
+            const bool big = a.n_rows >= (int64_t)148 * 24 * 128 || getenv("CR_SPMM_FORCE_BIG");   // (test knob: wide geometry on small graphs)
             const int rows_per_warp = big ? 128 : 32;
             const int64_t warps = (a.n_rows + rows_per_warp - 1) / rows_per_warp;
             // long-row chunks ride in the first CTAs of the same launch (the plan lives on the device: size by its upper bound)
@@ -456,12 +533,21 @@ int launch_spmm(const SpmmArgs& a) {
             // Bandwidth-bound graphs take the (GLPR, GU, GMINB) geometry; dataset-sized ones are latency bound and keep more rows
             // in flight per warp with the narrower groups (SLPR lanes x SNV float4, 4 gathers, 3 CTAs/SM): CiteULike-shaped
             // training step 0.37 ms vs 0.43 ms with the wide geometry.
-#define CR_GROUPED(L_, N_, V_, U_, B_)                                                                                          \
-    spmm_rows_grouped_kernel<L_, N_, V_, U_, B_><<<gblocks, kThreads, 0, a.stream>>>(                                           \
+            // multi-GPU: rows leave through shared-memory staging + TMA bulk stores (d <= 64: 32 KB of staging per CTA); the
+            // SM-issued stores remain for the NVLS multicast variant, wider rows and as an A/B knob (CR_SPMM_PEER_ST=1)
+            const bool staged = a.ep.peers && !a.ep.mc4 && GLPR * GNV <= 16 && !getenv("CR_SPMM_PEER_ST");
+#define CR_GROUPED_(L_, N_, V_, U_, B_, S_)                                                                                     \
+    spmm_rows_grouped_kernel<L_, N_, V_, U_, B_, S_><<<gblocks, kThreads, 0, a.stream>>>(                                       \
         a.rowptr, a.col, a.val, a.n_rows, a.X4, a.ep, long_row, rows_per_warp, a.hdr, a.chunks, a.partial4, chunk_ctas)
+#define CR_GROUPED(L_, N_, V_, U_, B_)                                                                                          \
+    do {                                                                                                                        \
+        if constexpr ((L_) * (N_) <= 16) { if (staged) CR_GROUPED_(L_, N_, V_, U_, B_, true); else CR_GROUPED_(L_, N_, V_, U_, B_, false); } \
+        else CR_GROUPED_(L_, N_, V_, U_, B_, false);                                                                            \
+    } while (0)
             if (big) { if (a.val) CR_GROUPED(GLPR, GNV, true, GU, GMINB); else CR_GROUPED(GLPR, GNV, false, GU, GMINB); }
             else { if (a.val) CR_GROUPED(SLPR, SNV, true, 4, 3); else CR_GROUPED(SLPR, SNV, false, 4, 3); }
 #undef CR_GROUPED
+#undef CR_GROUPED_
             CR_LAUNCH_CHECK("spmm_rows_grouped_kernel");
             cr::prof_stop(cr::PROF_SPMM_ROWS, a.stream);
         }

@@ -288,6 +288,14 @@ class ArrayDataBuilder:
                         mask_col=t_col[idx].astype(np.int32), gt_rowptr=gt_rowptr, gt_col=(gk - g_rows * n_i).astype(np.int32))
         return self._memo(("eval", split), make)
 
+    def split_of(self, data_set) -> Optional[str]:
+        """Name of the eval split whose (memoised) dict view ``data_set`` IS — how ``_evaluate(data_set, data_type)``, which
+        only gets the dict, finds its way back to the arrays.  None for any other object."""
+        for split in SPLITS:
+            if split != "training" and self._lazy.get(("dd", split, False)) is data_set:
+                return split
+        return None
+
     def eval_plan(self, split: str, data_type: str, cold_object: str, device):
         """The scorer's ``EvalPlan`` for a split ('warm_test', 'overall_valid', ...) without any per-user Python work."""
         import torch

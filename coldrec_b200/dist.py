@@ -331,7 +331,7 @@ class RowPartitionedGraph:
 
     def propagate_p2p(self, E0: torch.Tensor, n_layers: int, include_ego: bool = True, padded_io: bool = False,
                       copy: bool = True, sparse: bool = True, replicate_result: Optional[Sequence[int]] = None,
-                      multicast: bool = False) -> torch.Tensor:
+                      multicast: bool = False, layer_events: Optional[list] = None) -> torch.Tensor:
         """Same result as ``propagate``, but every finished row is stored by the SpMM epilogue straight into the
         gather table of the GPUs that read it (``cr_spmm_csr_bcast_f32``): the per-layer all-gather overlaps the SpMM
         instead of following it, and with ``sparse`` it only moves a row to the GPUs whose row block has a nonzero in
@@ -387,12 +387,20 @@ class RowPartitionedGraph:
                 n0 = mine[0][1] - mine[0][0]
                 off, split = mine[0][0], n0
                 off_hi = (mine[1][0] - n0) if len(mine) == 2 else 0
+            if layer_events is not None:     # (probe) CUDA events around each layer's kernels and its barrier
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                layer_events.append(ev)
+                ev[0].record()
             ops.spmm_bcast(rowptr, col0 if first else self.local.col, self.local.val, x, out_h.buffer_ptrs_dev, W, off, acc=acc,
                            acc_beta=(0.0 if (first and not include_ego) else 1.0), acc_div=(float(count) if last else 1.0),
                            plan=plan, bcast_acc=last, peer_row_split=split, peer_row_offset_hi=off_hi,
                            peer_need=(need_last if last else need),
                            multicast_ptr=(int(getattr(out_h, "multicast_ptr", 0) or 0) if multicast else 0))
+            if layer_events is not None:
+                layer_events[-1][1].record()
             out_h.barrier()                  # every GPU's rows have landed everywhere
+            if layer_events is not None:
+                layer_events[-1][2].record()
         if padded_io:
             res = src[2]
         else:

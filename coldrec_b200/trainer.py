@@ -65,7 +65,12 @@ class FusedEvalMixin:
         key = (id(data_set), data_type, str(self.device), self.args.cold_object)
         plan = st["plans"].get(key)
         if plan is None:
-            plan = EvalPlan.from_data(self.data, data_set, data_type, self.args.cold_object, st["device"])
+            # an ArrayDataBuilder knows the split this dict is a view of: its plan comes from arrays, no per-user Python work
+            split = self.data.split_of(data_set) if hasattr(self.data, "split_of") else None
+            if split is not None:
+                plan = self.data.eval_plan(split, data_type, self.args.cold_object, st["device"])
+            else:
+                plan = EvalPlan.from_data(self.data, data_set, data_type, self.args.cold_object, st["device"])
             st["plans"][key] = plan
         return plan
 

@@ -22,13 +22,22 @@ def _run(args, env=None, timeout=600):
 
 
 def test_reference_arm_line_and_non_zero_ranks_stay_silent():
-    small = ["--impl", "reference", "--steps", "2", "--warmup", "1", "--n-items", "30000", "--n-users", "4000", "--cpu-sample-users", "8"]
+    small = ["--impl", "reference", "--steps", "2", "--warmup", "1", "--n-items", "30000", "--n-users", "4000", "--cpu-sample-users", "8",
+             "--configs", "C2"]
     (line,) = _run(small)
     assert BASE_KEYS <= set(line) and line["impl"] == "reference"
     assert line["unit"] == "users/s" and line["higher_is_better"] is True and line["value"] > 0 and line["gpu_launches"] == 0
     assert line["steps"] == 2 and line["warmup"] == 1 and line["n_gpus"] == 1
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "8 users/step" in cb["sample"]
+    have_ref = os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "model", "BaseRecommender.py"))
+    # the reference's own _evaluate when baseline/_ref travelled with the snapshot, else the oracle port
+    assert cb["kind"] == ("reference" if have_ref else "port") and cb["cores"] >= 1 and cb["value"] == line["value"]
+    assert "8 users/step" in cb["sample"]
+    c2 = line["extra"]["C2"]
+    if have_ref:
+        assert c2["cpu_baseline"]["kind"] == "reference" and c2["value"] > 0 and "LGCN_Encoder.forward" in c2["cpu_baseline"]["sample"]
+    else:
+        assert "unavailable" in c2["cpu_baseline"]
     assert line["e2e"] == {"value": line["value"], "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
     # under torchrun only rank 0 runs the CPU arm; the other ranks exit 0 without a line
@@ -39,7 +48,7 @@ def test_reference_arm_line_and_non_zero_ranks_stay_silent():
 @pytest.mark.timeout(600)
 def test_b200_arm_line_at_toy_sizes():
     (line,) = _run(["--steps", "3", "--warmup", "3", "--n-items", "300000", "--n-users", "60000", "--users-per-step", "4096",
-                    "--graph-edges", "3000000", "--cpu-sample-users", "16", "--train-batch", "1024"])
+                    "--graph-edges", "3000000", "--cpu-sample-users", "16", "--train-batch", "1024", "--configs", "C1,C2", "--config-steps", "2"])
     assert BASE_KEYS <= set(line) and "impl" not in line
     assert line["unit"] == "users/s" and line["value"] > 0 and line["gpu_launches"] > 0 and line["vs_baseline"] is None
     assert line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
@@ -51,3 +60,8 @@ def test_b200_arm_line_at_toy_sizes():
         assert part["gpu_library_baseline"].get("value", 0) > 0, part["gpu_library_baseline"]
     assert line["lightgcn"]["unit"] == "edges/s" and line["lightgcn"]["gpu_launches"] > 0
     assert line["lightgcn"]["train_step"]["value"] > 0
+    for key in ("C1", "C2"):
+        x = line["extra"][key]
+        assert "error" not in x, x
+        assert x["value"] > 0 and x["gpu_launches"] > 0 and x["e2e"]["first_call_ms"] > 0 and x["roofline"]["kernel_launches_per_step"] > 0
+        assert x["cpu_baseline"].get("value", 0) > 0 and x["gpu_library_baseline"].get("value", 0) > 0, x

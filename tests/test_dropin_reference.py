@@ -99,16 +99,26 @@ def _reference_data(name="eval_item"):
     return ColdStartDataBuilder(*builder_args(g)), str(g["cold_object"])
 
 
-def _reference_eval(trainer, RB, kind, split):
+def _reference_twin(trainer, ref_cls):
+    """An instance of the UNTOUCHED reference class sharing the grafted trainer's state (tables, data, args): every method
+    it runs — _get_eval_cache, _evaluate, batch_predict — resolves in the reference's own MRO, none in the mixin's."""
+    twin = object.__new__(ref_cls)
+    twin.__dict__.update({k: v for k, v in trainer.__dict__.items() if k != "_fused"})
+    twin._eval_cache = {}
+    assert "FusedEvalMixin" not in [c.__name__ for c in type(twin).__mro__]
+    return twin
+
+
+def _reference_eval(trainer, ref_cls, kind, split, rec_only=False):
     """The reference's own _evaluate (its torch path on the trainer's device) + its own ranking_evaluation."""
     from util.evaluator import ranking_evaluation
-    gt = getattr(trainer.data, f"{ {'all': 'overall'}.get(kind, kind) }_{split}_set")
-    rec = RB.BaseColdStartTrainer._evaluate(trainer, gt, kind)
-    return ranking_evaluation(gt, rec, trainer.topN if split == "test" else [trainer.max_N])
+    twin = _reference_twin(trainer, ref_cls)
+    gt = getattr(twin.data, f"{ {'all': 'overall'}.get(kind, kind) }_{split}_set")
+    rec = twin._evaluate(gt, kind)
+    return rec if rec_only else ranking_evaluation(gt, rec, twin.topN if split == "test" else [twin.max_N])
 
 
 def _run_grafted(cls_name, make_cls, epochs=2):
-    import model.BaseRecommender as RB
     from coldrec_b200 import FusedEvalMixin
     data, cold_object = _reference_data()
     Fused = make_cls(FusedEvalMixin)
@@ -116,9 +126,8 @@ def _run_grafted(cls_name, make_cls, epochs=2):
     import random
     random.seed(7)
     t = Fused(_Cfg(_args(cls_name, epochs, 0, cold_object), data, "cuda:0"))
-    t._eval_cache = {}                       # what the reference's __init__ sets; its _evaluate (used as the checker) needs it
     _, out = _quiet(t.run)
-    return t, RB, out
+    return t, out
 
 
 @pytest.mark.gpu
@@ -135,23 +144,23 @@ def test_mixin_on_reference_mf_run_equals_reference_evaluation():
                 type(self).epoch_lines.append(lines)
                 return lines
         return MF
-    t, RB, out = _run_grafted("MF", make)
+    t, out = _run_grafted("MF", make)
     assert type(t).__mro__[1].__name__ == "FusedEvalMixin" and t.epochs_ran == 2
     assert "Testing under [cold] setting..." in out and "[warm setting] The result of MF:" in out
     # final results of the three settings == the reference's own evaluation of the same (best) tables
     for kind, attr in (("all", "overall_test_results"), ("cold", "cold_test_results"), ("warm", "warm_test_results")):
-        measure, perf = _reference_eval(t, RB, kind, "test")
+        measure, perf = _reference_eval(t, RefMF, kind, "test")
         assert getattr(t, attr) == perf, f"{kind}: {getattr(t, attr)} vs reference {perf}"
         assert f"[{kind} setting] The result of MF:\n{''.join(measure)}" in out
     # per-epoch validation lines == the reference's, on the tables of that epoch
     for (ue, ie), lines in zip(type(t).epoch_tables, type(t).epoch_lines):
         t.user_emb, t.item_emb = ue, ie
-        measure, _ = _reference_eval(t, RB, "all", "valid")
+        measure, _ = _reference_eval(t, RefMF, "all", "valid")
         assert lines == [m.strip() for m in measure[1:]]
     # the lazily built rec list is the reference's dict format
     t.user_emb, t.item_emb = t.best_user_emb, t.best_item_emb
     rec = t.test("all")
-    ref_rec = RB.BaseColdStartTrainer._evaluate(t, t.data.overall_test_set, "all")
+    ref_rec = _reference_eval(t, RefMF, "all", "test", rec_only=True)
     assert list(rec.keys()) == list(ref_rec.keys())
     u0 = next(iter(ref_rec))
     assert [i for i, _ in rec[u0]] == [i for i, _ in ref_rec[u0]]
@@ -161,7 +170,8 @@ def test_mixin_on_reference_mf_run_equals_reference_evaluation():
 @pytest.mark.gpu
 def test_mixin_on_reference_lightgcn_with_csr_graph_swapped_in():
     refimport.import_reference()
-    import model.LightGCN as RL
+    import importlib
+    RL = importlib.import_module("model.LightGCN")            # (`model.LightGCN` the attribute is the trainer class: model/__init__.py)
     from coldrec_b200 import CsrGraph, propagate
 
     class FusedEncoder(RL.LGCN_Encoder):                       # the eval-time forward on the fused SpMM
@@ -180,14 +190,14 @@ def test_mixin_on_reference_lightgcn_with_csr_graph_swapped_in():
                 torch.manual_seed(11)
                 self.model = FusedEncoder(self.data, self.emb_size, self.n_layers, self.device)
         return LightGCN
-    t, RB, out = _run_grafted("LightGCN", make)
+    t, out = _run_grafted("LightGCN", make)
     with torch.no_grad():                                      # the reference encoder's own forward on the trained parameters
         ref_u, ref_i = RL.LGCN_Encoder.forward(t.model)
     for got, ref in ((t.best_user_emb, ref_u), (t.best_item_emb, ref_i)):
         assert (got - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
     t.user_emb, t.item_emb = ref_u, ref_i
     for kind, attr in (("all", "overall_test_results"), ("cold", "cold_test_results"), ("warm", "warm_test_results")):
-        _, perf = _reference_eval(t, RB, kind, "test")
+        _, perf = _reference_eval(t, RL.LightGCN, kind, "test")
         assert getattr(t, attr) == perf, f"{kind}: {getattr(t, attr)} vs reference {perf}"
 
 

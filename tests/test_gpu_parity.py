@@ -244,15 +244,19 @@ def test_reevaluation_after_item_table_is_freed_and_reallocated():
     data = O.OracleData(*builder_args(g))
     tr = _trainer(data, "item", PRECISIONS[1], base=AldiScoreTables)
     rng = np.random.default_rng(5)
-    seen_ptrs = set()
+    tr.item_emb = None
     for epoch in range(6):
         I = (rng.standard_normal(g["item_emb"].shape) * 0.1).astype(np.float32)
         Uw = (rng.standard_normal(g["user_emb"].shape) * 0.1).astype(np.float32)
         Uc = (rng.standard_normal(g["user_emb"].shape) * 0.1).astype(np.float32)
-        tr.item_emb = None                                   # free last epoch's block first, like a rebinding trainer
-        tr.item_emb = cu(I).clone()
+        if epoch % 2 == 1:                                   # same storage, same _version, new contents (ALDI's `.data[...] = ...`):
+            key = (tr.item_emb.data_ptr(), tr.item_emb._version)
+            tr.item_emb.data.copy_(cu(I))                    # exactly the state an (address, version) key cannot tell apart
+            assert key == (tr.item_emb.data_ptr(), tr.item_emb._version)
+        else:                                                # a rebinding trainer: last epoch's block freed, a new one allocated
+            tr.item_emb = None
+            tr.item_emb = cu(I).clone()
         tr.warm_user_emb, tr.cold_user_emb = cu(Uw), cu(Uc)
-        seen_ptrs.add(tr.item_emb.data_ptr())
         for typ in ("cold", "warm"):
             rec = tr.test(typ)
             users = list(getattr(data, f"{typ}_test_set").keys())
@@ -264,7 +268,6 @@ def test_reevaluation_after_item_table_is_freed_and_reallocated():
             for j in range(len(users)):
                 want = np.asarray(exact(j, got_i[j]), dtype=np.float32)
                 assert np.allclose(got_s[j], want, atol=1e-5), f"epoch {epoch} {typ} user {j}: scores are not this epoch's"
-    assert len(seen_ptrs) < 6, "the allocator never reused an address: the scenario was not exercised"
 
 
 @pytest.mark.parametrize("precision", PRECISIONS, ids=["exact", "tf32"])
