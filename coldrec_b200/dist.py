@@ -187,6 +187,56 @@ class GridShardedFullRankScorer(ShardedFullRankScorer):
         return self._merge(gs[:, lo:hi].contiguous(), gi[:, lo:hi].contiguous())
 
 
+class ShardedItemGenerator:
+    """Content -> embedding generators over an item-sharded catalogue.  Tower rows are independent, so
+    rank r runs the tower on ITS rows of the content (and backbone) tables only and the generated tile is directly the
+    item shard its local scorer sweeps — no collective, tower weights replicated (<= 2.4 MB).  ``scorer`` is a
+    ``GridShardedFullRankScorer`` / ``ShardedFullRankScorer`` (the item range is the scorer's).
+
+      * whole-table generators (DropoutNet / Heater item side, model/DropoutNet.py:192-213, model/Heater.py:187-223):
+        ``generate(fn, *row_tables)`` = ``fn(*[t[ib:ie] for t in row_tables])``;
+      * cold-row overwrite (GAR / ALDI / DeepMusic / MetaEmbedding, model/GAR.py:44-46, model/ALDI.py:89-97):
+        ``overwrite_cold(fn, item_shard, content_shard, cold_ids)`` generates only the cold ids that fall in this rank's
+        range and scatters them into its shard in place (``fn(content_shard, rows, out)`` — the signature of
+        ``towers.gar_generate`` / ``towers.aldi_tower`` with the state bound).
+    """
+
+    def __init__(self, scorer, n_items: int):
+        self.scorer, self.n_items = scorer, int(n_items)
+        self.item_begin, self.item_end = scorer.item_range(n_items) if hasattr(scorer, "item_range") else \
+            shard_range(n_items, scorer.rank, scorer.world)
+
+    def rows(self, table: torch.Tensor) -> torch.Tensor:
+        """This rank's rows of a full (n_items, *) table; a table that already has shard length is taken as the shard."""
+        if table.shape[0] == self.item_end - self.item_begin and table.shape[0] != self.n_items:
+            return table
+        if table.shape[0] != self.n_items:
+            raise ValueError(f"table has {table.shape[0]} rows, expected {self.n_items} (full) or {self.item_end - self.item_begin} (shard)")
+        return table[self.item_begin:self.item_end]
+
+    def generate(self, fn: Callable, *row_tables: torch.Tensor) -> torch.Tensor:
+        out = fn(*[self.rows(t).contiguous() for t in row_tables])
+        if out.shape[0] != self.item_end - self.item_begin:
+            raise ValueError("the generator must return one row per item of the shard")
+        return out
+
+    def local_cold_rows(self, cold_ids) -> torch.Tensor:
+        """Cold item ids inside this rank's range, as int32 row numbers of the shard (on the device of ``cold_ids``)."""
+        ids = torch.as_tensor(cold_ids)
+        sel = ids[(ids >= self.item_begin) & (ids < self.item_end)]
+        return (sel - self.item_begin).to(torch.int32).contiguous()
+
+    def overwrite_cold(self, fn: Callable, item_shard: torch.Tensor, content_shard: torch.Tensor, cold_ids) -> torch.Tensor:
+        rows = self.local_cold_rows(cold_ids).to(item_shard.device)
+        if rows.numel():
+            fn(self.rows(content_shard), rows, item_shard)
+        return item_shard
+
+    def topk(self, user_tab, item_shard, plan: EvalPlan, item_flags=None):
+        """Rank the eval users against the generated catalogue: local sweep over this rank's tile + the scorer's exchange."""
+        return self.scorer.topk(user_tab, item_shard, self.item_begin, plan, item_flags)
+
+
 class RowPartitionedGraph:
     """A square adjacency split by rows over the ranks of ``group`` with padded node numbering.
 

@@ -421,3 +421,78 @@ def test_partition_helpers():
     assert b[0] == 0 and b[-1] == 7 and all(x <= y for x, y in zip(b, b[1:]))
     nnz = [rowptr[b[i + 1]] - rowptr[b[i]] for i in range(4)]
     assert max(nnz) <= 200
+
+
+# ---------------------------------------------------------------------------------------------- sharded generators
+def _gen_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from coldrec_b200.dist import GridShardedFullRankScorer, ShardedItemGenerator
+        from coldrec_b200.scoring import EvalPlan
+        c = _case()
+        Ut, It = torch.from_numpy(c["U"]), torch.from_numpy(c["I"])
+        plan = EvalPlan.from_arrays(torch.from_numpy(c["uids"]), torch.from_numpy(c["rowptr"]), torch.from_numpy(c["col"]),
+                                    torch.from_numpy(c["gt_rowptr"]), torch.from_numpy(c["gt_col"]))
+        content, W1, cold = _gen_inputs(c)
+        out = {}
+        for S in [s_ for s_ in (1, 2, 4) if world % s_ == 0]:
+            sc = GridShardedFullRankScorer(c["K"], S, **_cpu_scoring_callables(c["K"]))
+            gen = ShardedItemGenerator(sc, c["n_items"])
+            # whole-table generator (DropoutNet / Heater style): [V | content] rows of this rank only
+            shard = gen.generate(lambda V, C: _tower(torch.cat([V, C], 1), W1), It, content)
+            s, i = gen.topk(Ut, shard, plan)
+            # cold-row overwrite (GAR / ALDI style) into this rank's slice of the backbone table
+            base = gen.rows(It).clone()
+            def scatter(cont, rows, out_):
+                out_[rows.long()] = _tower(torch.cat([out_[rows.long()], cont[rows.long()]], 1), W1)
+            gen.overwrite_cold(scatter, base, content, cold)
+            s2, i2 = gen.topk(Ut, base, plan)
+            lo, hi = sc.user_slice(plan.n_q)
+            out[S] = dict(i=i.numpy(), s=s.numpy(), i2=i2.numpy(), lo=lo, hi=hi, rows=(gen.item_begin, gen.item_end),
+                          n_cold_local=int(gen.local_cold_rows(cold).numel()))
+        ret[rank] = out
+    finally:
+        dist.destroy_process_group()
+
+
+def _tower(x, W1):
+    return torch.tanh(x.double() @ W1.double().T).float()
+
+
+def _gen_inputs(c):
+    g = torch.Generator().manual_seed(12)
+    content = torch.randn(c["n_items"], 24, generator=g)
+    W1 = torch.randn(64, 64 + 24, generator=g) * 0.2
+    cold = torch.sort(torch.randperm(c["n_items"], generator=g)[:c["n_items"] // 5]).values
+    return content, W1, cold
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_generators_feed_the_local_scorer(world):
+    """each rank generates only its item range (whole-table towers and the cold-row overwrite); the ranked
+    lists equal generating the whole catalogue on one device and sweeping it once."""
+    ret = mp.Manager().dict()
+    mp.spawn(_gen_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    c = _case()
+    K = c["K"]
+    Ut, It = torch.from_numpy(c["U"]), torch.from_numpy(c["I"])
+    content, W1, cold = _gen_inputs(c)
+    full_a = _tower(torch.cat([It, content], 1), W1)
+    full_b = It.clone()
+    full_b[cold] = _tower(torch.cat([It[cold], content[cold]], 1), W1)
+    want = []
+    for tab in (full_a, full_b):
+        sc = _scores(Ut[torch.from_numpy(c["uids"]).long()], tab)
+        for j in range(len(c["uids"])):
+            sc[j, c["col"][c["rowptr"][j]:c["rowptr"][j + 1]]] = O.MASK_SENTINEL
+        want.append(_sorted_topk(sc, np.broadcast_to(np.arange(c["n_items"], dtype=np.int32), sc.shape), K)[1])
+    for S in [s_ for s_ in (1, 2, 4) if world % s_ == 0]:
+        n_cold = {}
+        for r in range(world):
+            o = ret[r][S]
+            assert np.array_equal(o["i"], want[0][o["lo"]:o["hi"]]), f"S={S} rank {r}: whole-table generator"
+            assert np.array_equal(o["i2"], want[1][o["lo"]:o["hi"]]), f"S={S} rank {r}: cold-row overwrite"
+            n_cold[o["rows"]] = o["n_cold_local"]
+        assert sum(n_cold.values()) == len(cold), "every cold item is generated by exactly one item shard"

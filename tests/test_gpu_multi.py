@@ -36,8 +36,12 @@ def _case():
     gt_col = np.concatenate(gt).astype(np.int32)
     eu, ei = rng.integers(0, n_users, 200000), rng.integers(0, n_items, 200000)
     ei[:3000] = 7                       # one long row (> 512 nonzeros) so the split path crosses the partition too
+    content = rng.standard_normal((n_items, 40)).astype(np.float32)
+    gar = {"0.weight": (rng.standard_normal((128, 40)) * 0.2).astype(np.float32), "0.bias": np.zeros(128, np.float32),
+           "2.weight": (rng.standard_normal((64, 128)) * 0.2).astype(np.float32), "2.bias": np.zeros(64, np.float32)}
+    cold = np.sort(rng.choice(n_items, n_items // 5, replace=False)).astype(np.int64)
     return dict(U=U, I=I, uids=uids, rowptr=rowptr, col=col, gt_rowptr=gt_rowptr, gt_col=gt_col, eu=eu, ei=ei,
-                n_users=n_users, n_items=n_items)
+                n_users=n_users, n_items=n_items, content=content, gar=gar, cold=cold)
 
 
 def _worker(rank, world, port, ret):
@@ -64,6 +68,17 @@ def _worker(rank, world, port, ret):
             gb, ge = gsc.item_range(c["n_items"])
             g_s, g_i = gsc.topk(t(c["U"]), t(c["I"][gb:ge].copy()), gb, plan)
             grid[S] = (g_i.cpu().numpy(), gsc.user_slice(plan.n_q), gsc.metrics(g_i, plan, [10, 20], rounded=False))
+        # generators over the item-sharded catalogue: each rank generates its rows, feeds its local sweep
+        from coldrec_b200 import towers
+        from coldrec_b200.dist import ShardedItemGenerator
+        gst = {k: t(v) for k, v in c["gar"].items()}
+        gen = ShardedItemGenerator(GridShardedFullRankScorer(20, world, ops.SCORE_TF32_CHECKED), c["n_items"])
+        shard = gen.generate(lambda C: towers.gar_generate(gst, C), t(c["content"]))
+        _, gen_i = gen.topk(t(c["U"]), shard, plan)
+        base = gen.rows(t(c["I"])).clone()
+        gen.overwrite_cold(lambda C, rows, out: towers.gar_generate(gst, C, rows=rows, out=out), base, t(c["content"]), t(c["cold"]))
+        _, gen_i2 = gen.topk(t(c["U"]), base, plan)
+        gen_out = dict(i=gen_i.cpu().numpy(), i2=gen_i2.cpu().numpy(), slice=gen.scorer.user_slice(plan.n_q))
         adj = O.normalize_graph_mat(O.bipartite_adjacency(c["eu"], c["ei"], c["n_users"], c["n_items"])).tocsr()
         adj.sort_indices()
         G = RowPartitionedGraph(adj.indptr.astype(np.int64), adj.indices.astype(np.int64), adj.data.astype(np.float32), dev,
@@ -87,7 +102,7 @@ def _worker(rank, world, port, ret):
         (ub, ue), (ib, ie) = G.parts[rank]
         ret[rank] = dict(s=s.cpu().numpy(), i=i.cpu().numpy(), lo=lo, hi=hi, perf=perf, nccl=out_nccl, p2p=out_p2p, p2p_b=out_p2p_b,
                          p2p_c=out_p2p_c, p2p_d=out_p2p_d, p2p_e=out_p2p_e, p2p_f=out_p2p_f, p2p_g=out_p2p_g, p2p_h=out_p2p_h, p2p_i=out_p2p_i, own_items=(ib, ie), has_multicast=G.has_multicast,
-                         need_copies=G.need_copies, grid=grid)
+                         need_copies=G.need_copies, grid=grid, gen=gen_out)
     finally:
         dist.destroy_process_group()
 
@@ -116,6 +131,19 @@ def test_multi_gpu_sharded_scoring_and_fused_allgather_propagation(world):
         for S, (g_i, (glo, ghi), g_perf) in ret[r]["grid"].items():
             assert np.array_equal(g_i, i1[glo:ghi]) and np.allclose(g_perf, want, atol=1e-9), f"grid S={S} rank {r}"
         assert np.allclose(ret[r]["perf"], want, atol=1e-9)
+    # sharded generators == generate the whole catalogue on one GPU, sweep once
+    from coldrec_b200 import towers
+    gst = {k: t(v) for k, v in c["gar"].items()}
+    full_a = towers.gar_generate(gst, t(c["content"]))
+    full_b = t(c["I"]).clone()
+    towers.gar_generate(gst, t(c["content"]), rows=t(c["cold"]).to(torch.int32), out=full_b)
+    kw = dict(user_ids=t(c["uids"]), mask_rowptr=t(c["rowptr"]), mask_col=t(c["col"]), precision=ops.SCORE_EXACT_F32)
+    want_a = ops.score_topk(t(c["U"]), full_a, 20, **kw)[1].cpu().numpy()
+    want_b = ops.score_topk(t(c["U"]), full_b, 20, **kw)[1].cpu().numpy()
+    for r in range(world):
+        lo, hi = ret[r]["gen"]["slice"]
+        assert np.array_equal(ret[r]["gen"]["i"], want_a[lo:hi]), f"rank {r}: sharded whole-table generator + sweep"
+        assert np.array_equal(ret[r]["gen"]["i2"], want_b[lo:hi]), f"rank {r}: sharded cold-row overwrite + sweep"
     adj = O.normalize_graph_mat(O.bipartite_adjacency(c["eu"], c["ei"], c["n_users"], c["n_items"]))
     Ut, It = torch.from_numpy(c["U"]), torch.from_numpy(c["I"])
     ref = torch.cat(O.propagate(adj, Ut, It, 3)).numpy()
