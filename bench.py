@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--graph-edges", type=int, default=GRAPH_EDGES)
     ap.add_argument("--cpu-sample-users", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-robustness", action="store_true", help="skip the robustness lines (N=1: warm/cold settings, duplicate rows, "
+                                                                 "heavy-tailed / norm-sorted item tables; under \"robustness\")")
     ap.add_argument("--configs", default="C1,C2,C3", help="dataset-shaped side lines under \"extra\" (N=1 only): any of C1,C2,C3")
     ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C2 / C3 dataset-shaped lines")
     ap.add_argument("--config-steps", type=int, default=5)
@@ -132,12 +134,23 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def ncu_traffic(key):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
+def ncu_traffic(key, src):
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
+    capture, profiles/r02_traffic.json, written by tools/ncu_traffic.py).  DRAM counters cannot be read without a profiler,
+    so the figure is a committed measurement — but one pinned to the kernel source it was taken on: the file records the
+    sha256 of coldrec_b200/csrc/<src>, and when that no longer matches the tree the figure is withheld (null) and the
+    reason reported, instead of going stale silently.  Returns (bytes | None, note | None)."""
+    import hashlib
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(key)
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(key)
     except OSError:
-        return None
+        return None, "no committed ncu capture (profiles/r02_traffic.json)"
+    if not rec:
+        return None, f"no committed ncu capture of {key}"
+    sha = hashlib.sha256(open(os.path.join(ROOT, "coldrec_b200", "csrc", src), "rb").read()).hexdigest()
+    if rec.get("source_sha256") != sha:
+        return None, f"stale: the committed capture was taken on another revision of csrc/{src} — re-capture (tools/gpu_prof.sh)"
+    return rec["bytes_per_launch"], None
 
 
 def make_step_plans(n_steps, n_q, n_users, n_items, seed, device):
@@ -256,10 +269,14 @@ def run_b200(args):
         achieved = flops / (sweep_ms * 1e-3) / 1e12 if sweep_ms > 0 else 0.0
         roofline = {"bound": "tensor", "kernel": "score_sweep_tc_kernel", "achieved": round(achieved, 1), "peak": round(tf32_peak, 1),
                     "unit": "TFLOP/s", "frac": round(achieved / tf32_peak, 4),
-                    "traffic": ncu_traffic("score_sweep_tc_kernel_bytes_per_launch") if (world == 1 and n_q == USERS_PER_STEP and args.n_items == N_ITEMS) else None,
+                    "traffic": None,
                     "peak_source": f"{pk_src} bf16_tflops_sustained/2 (TF32 dense is half the bf16 rate)",
                     "launch_ms": round(sweep_ms, 3), "launches": cnt.value, "flop_per_launch": flops,
                     "share_of_step": round(sweep_ms * cnt.value / ms, 4)}
+        if world == 1 and n_q == USERS_PER_STEP and args.n_items == N_ITEMS:
+            roofline["traffic"], note = ncu_traffic("score_sweep_tc_kernel", "score_tc.cu")
+            if note:
+                roofline["traffic_note"] = note
 
         # end to end through the host-buffer API: H2D of the step's plan from pinned memory, D2H of top-K + metric sums
         hb = HostBatchEvaluator(scorer, TOPN, n_q, n_q * MASK_PER_USER, n_q * GT_PER_USER, device)
@@ -295,6 +312,8 @@ def run_b200(args):
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_score_baseline(user_tab, item_shard, plans_d[W], args.cpu_sample_users)
             out["gpu_library_baseline"] = library_score_baseline(user_tab, item_shard, plans_d[W])
+        if world == 1 and not args.no_robustness:
+            out["robustness"] = run_robustness(args, lib, user_tab, item_shard, distinct_plans, device, pk)
         del item_shard, plans, plans_d, host_plans, hb, distinct, distinct_plans, pinned
         torch.cuda.empty_cache()
 
@@ -423,11 +442,15 @@ def run_lightgcn(args, device, rank, world, pk, pk_src, lib):
                gpu_launches=int(launches),
                roofline={"bound": "hbm", "kernel": "spmm_rows_grouped_kernel (rows + long-row chunks in one launch; + spmm_long_reduce_kernel)", "achieved": round(step_gbs, 1),
                          "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(step_gbs / pk["hbm_gbs"], 4),
-                         "traffic": ncu_traffic("spmm_rows_grouped_kernel_bytes_per_launch") if (world == 1 and args.graph_edges == GRAPH_EDGES) else None,
+                         "traffic": None,
                          "peak_source": f"{pk_src} hbm_gbs (copy bandwidth)", "bytes_per_layer": bytes_layer,
                          "rows_kernel_ms": round(rows_ms, 3), "rows_kernel_launches": cnt.value,
                          "share_of_step": round(tot.value / ms, 4)},
                clocks=clk.summary())
+    if world == 1 and args.graph_edges == GRAPH_EDGES:
+        out["roofline"]["traffic"], note = ncu_traffic("spmm_rows_grouped_kernel", "spmm.cu")
+        if note:
+            out["roofline"]["traffic_note"] = note
     if world > 1:
         out["check"] = check_partitioned_propagation(G, E0u, E0i, res, PG, args, device, world)
         out["nvlink"] = nvlink_bytes(PG, args, ms / Ksteps, device, world)
@@ -481,6 +504,86 @@ def run_train_step(args, device, G, E0u, E0i, pk, lib):
             "loss": [round(x, 6) for x in loss.cpu().tolist()[:3]], "sampler_exhausted": int(smp.n_exhausted.item())}
 
 
+
+
+# ------------------------------------------------------------------------------------------- robustness lines (N = 1)
+def run_robustness(args, lib, user_tab, item_tab, plans, device, pk, steps=3, warmup=1):
+    """The same sweep on inputs the headline line does not cover: the 'warm' / 'cold' settings with 20 % cold
+    items through BOTH mask paths (item flags tested inside the kernel's bitmap producer; flagged items compacted away
+    before the sweep, ids recovered through ``item_gids``), 1 % exactly duplicated item rows (score ties), log-normal item
+    norms (sigma = 1: stresses the margin proof, whose eps scales with the largest item norm) and the same table sorted by
+    ascending norm (the thresholds keep rising to the end of the sweep).  ``n_refined`` = queries whose margin proof failed
+    and were re-ranked by the exact fp32 kernel, summed over ALL timed steps."""
+    import ctypes
+    from coldrec_b200 import ops
+    from coldrec_b200.scoring import EvalPlan, FullRankScorer, FLAG_COLD, FLAG_WARM
+    n_items, n_q = item_tab.shape[0], plans[0].n_q
+    g = torch.Generator(device=device).manual_seed(77)
+    flags = torch.where(torch.rand(n_items, device=device, generator=g) < 0.2, FLAG_COLD, FLAG_WARM).to(torch.uint8)
+    tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+    lines = []
+
+    def timed(name, fn, n_swept):
+        for k in range(warmup):
+            fn(plans[k % len(plans)])
+        torch.cuda.synchronize(device)
+        lib.cr_profile_enable(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nref = torch.zeros(1, dtype=torch.int64, device=device)
+        e0.record()
+        for k in range(steps):
+            for r in fn(plans[(warmup + k) % len(plans)]):
+                nref += r.to(torch.int64)
+        e1.record()
+        torch.cuda.synchronize(device)
+        tot, cnt = ctypes.c_double(), ctypes.c_int()
+        lib.cr_profile_read(0, ctypes.byref(tot), ctypes.byref(cnt)); lib.cr_profile_enable(0)
+        ms = e0.elapsed_time(e1) / steps
+        sweep_ms = tot.value / max(cnt.value, 1)
+        tfl = 2.0 * n_q * n_swept * D / (sweep_ms * 1e-3) / 1e12 if sweep_ms > 0 else 0.0
+        lines.append({"case": name, "users_per_s": round(n_q / (ms * 1e-3), 1), "ms_per_step": round(ms, 3), "items_swept": int(n_swept),
+                      "sweep_ms": round(sweep_ms, 3), "sweep_tflops": round(tfl, 1), "sweep_frac_of_tf32_sustained": round(tfl / tf32_peak, 4),
+                      "n_refined_all_steps": int(nref.item()), "queries_all_steps": n_q * steps})
+
+    def kernel_flags(excl):
+        def fn(p):
+            s, i, nref = ops.score_topk(user_tab, item_tab, K, user_ids=p.user_ids, mask_rowptr=p.mask_rowptr, mask_col=p.mask_col,
+                                        item_flags=flags if excl else None, flag_exclude=excl, precision=ops.SCORE_TF32_CHECKED)
+            ops.rank_metrics(i, p.gt_rowptr, p.gt_col, TOPN)
+            return [nref]
+        return fn
+
+    def compacted(excl):
+        fr = FullRankScorer(K, ops.SCORE_TF32_CHECKED)
+        def fn(p):
+            q = EvalPlan(None, p.user_ids, p.mask_rowptr, p.mask_col, p.gt_rowptr, p.gt_col, excl)
+            s, i = fr.topk([(user_tab, item_tab, None)], q, flags)
+            ops.rank_metrics(i, p.gt_rowptr, p.gt_col, TOPN)
+            return fr.n_refined
+        return fn
+    n_warm, n_cold = int((flags == FLAG_WARM).sum()), int((flags == FLAG_COLD).sum())
+    timed("all (no flag mask; the headline case)", kernel_flags(0), n_items)
+    timed("warm setting, 20% cold items masked inside the kernel (flag byte per item)", kernel_flags(FLAG_COLD), n_items)
+    timed("warm setting, cold items compacted away before the sweep (item_gids)", compacted(FLAG_COLD), n_warm)
+    timed("cold setting, 80% warm items masked inside the kernel", kernel_flags(FLAG_WARM), n_items)
+    timed("cold setting, warm items compacted away before the sweep (item_gids)", compacted(FLAG_WARM), n_cold)
+    saved = item_tab.clone()
+    try:
+        nd = n_items // 100
+        perm = torch.randperm(n_items, device=device, generator=g)
+        item_tab[perm[:nd]] = item_tab[perm[nd:2 * nd]]
+        timed("1% of the item rows exact duplicates of other rows (score ties)", kernel_flags(0), n_items)
+        item_tab.copy_(saved)
+        item_tab *= torch.exp(torch.randn(n_items, 1, device=device, generator=g))
+        timed("log-normal item norms (sigma = 1)", kernel_flags(0), n_items)
+        order = torch.argsort((item_tab * item_tab).sum(1))
+        item_tab.copy_(item_tab[order])
+        del order
+        timed("log-normal item norms, table sorted by ascending norm", kernel_flags(0), n_items)
+    finally:
+        item_tab.copy_(saved)
+        del saved
+    return lines
 
 # ------------------------------------------------------------------------------------------- multi-GPU result checks
 def check_sharded_ids(args, scorer, user_tab, item_shard, ib, plan, S, device, world, n_sample=4096):

@@ -36,11 +36,11 @@
 
 namespace {
 
-constexpr int kD = 64;                  // embedding width served by this path
 constexpr int kBM = 256;                // queries per unit (2 x 128-row MMA tiles)
-// Tile geometry knobs (tools/build_variant.sh): 512 TMEM columns = 128 (queries) + kAcc x 2 x kBN, so the alternatives to
-// 96-item tiles x 2 accumulator stages are 64 x 3 (a third stage decouples the MMA issuer from the slowest epilogue warp —
-// the lever DESIGN.md K1 names for short shards; untested at the time of writing) and 32 x 6.
+// Tile geometry knobs of the d = 64 instantiation (tools/build_variant.sh): 512 TMEM columns = 2 x 64 (queries) + kAcc x 2 x kBN.
+// r02 A/B on one box (TFLOP/s at 10M / 2.5M / 1.25M items per shard): 96 x 2 accumulator stages 674 / 620 / 551;
+// 64 x 3 stages 567 / 544 / 510 (the N=64 MMA is less efficient than N=96 and the third stage does not pay it back);
+// 32 x 6 stages 347 / 337 / 327.  96 x 2 stays.
 #ifndef CR_TC_BN
 #define CR_TC_BN 96
 #endif
@@ -50,12 +50,6 @@ constexpr int kBM = 256;                // queries per unit (2 x 128-row MMA til
 #ifndef CR_TC_STAGES
 #define CR_TC_STAGES 6
 #endif
-constexpr int kBN = CR_TC_BN;           // items per tile
-constexpr int kChunks = kBN / 32;       // 32-column epilogue chunks per tile
-constexpr int kStages = CR_TC_STAGES;   // item smem ring
-constexpr int kAcc = CR_TC_ACC;         // TMEM accumulator stages
-static_assert(kBN % 32 == 0 && kBN >= 32 && 128 + kAcc * 2 * kBN <= 512, "TMEM: 128 query columns + kAcc x 2 x kBN accumulator columns");
-static_assert(8 * kChunks <= 32, "the mask producer's dirty-word bitmap holds 8 queries x kChunks bits per lane");
 #ifndef CR_MASK_STAGES
 #define CR_MASK_STAGES 4
 #endif
@@ -63,12 +57,41 @@ constexpr int kMaskStages = CR_MASK_STAGES;          // mask-bitmap ring (decoup
                                         // epilogue waiting 40 % of its time on a bitmap tied to the 2 TMEM stages)
 constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;            // first epilogue warp
-constexpr int kChunkBytes = kBN * 128;  // one SWIZZLE_128B box: 96 rows x 32 fp32
-constexpr int kTileBytes = 2 * kChunkBytes;
-constexpr int kTmemA = 0;               // query tiles: columns [0, 128)
-constexpr int kTmemAcc = 128;           // accumulators: 128 + a*192 + t*96
 constexpr float kEpsFactor = 2.1e-3f;   // > 2^-9 (1 + 2^-10) + fp32 accumulation slack
 constexpr uint32_t kSpinLimit = 1u << 26;
+
+// Geometry of one instantiation.  D = 64: the MF / LightGCN / generator tables (kBN = 96, two accumulator stages, 6-stage
+// item ring).  D = 128: VBPR / AMR's concatenated tables (model/VBPR.py:68-75): the two query tiles take 2 x 128 TMEM
+// columns, which leaves 2 stages x 2 tiles x 64 accumulator columns; a 64-item tile is 32 KB (four SWIZZLE_128B boxes),
+// five of them in flight; 2 x 16 MMAs (M128 N64 K8) per tile.
+template <int D>
+struct Geo {
+    static_assert(D == 64 || D == 128, "instantiated widths");
+    static constexpr int kD = D;
+    static constexpr int kBN = D == 64 ? CR_TC_BN : 64;          // items per tile
+    static constexpr int kAcc = D == 64 ? CR_TC_ACC : 2;         // TMEM accumulator stages
+    static constexpr int kStages = D == 64 ? CR_TC_STAGES : 5;   // item smem ring
+    static constexpr int kChunks = kBN / 32;                     // 32-column epilogue chunks per tile
+    static constexpr int kBoxes = D / 32;                        // SWIZZLE_128B boxes (32 fp32 wide) per item tile
+    static constexpr int kChunkBytes = kBN * 128;                // one box: kBN rows x 32 fp32
+    static constexpr int kTileBytes = kBoxes * kChunkBytes;
+    static constexpr int kTmemA = 0;                             // query tiles: columns [0, 2 D)
+    static constexpr int kTmemAcc = 2 * D;                       // accumulators: 2 D + a * 2 kBN + t * kBN
+    static_assert(kBN % 32 == 0 && kBN >= 32 && 2 * D + kAcc * 2 * kBN <= 512, "TMEM: 2 D query columns + kAcc x 2 x kBN accumulator columns");
+    static_assert(8 * kChunks <= 32, "the mask producer's dirty-word bitmap holds 8 queries x kChunks bits per lane");
+    // kind::tf32 instruction descriptor: D=F32, A=B=TF32, both K-major, N=kBN, M=128.
+    static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    struct Smem {
+        static constexpr int kB = 0;                                       // kStages x kTileBytes
+        static constexpr int kMask = kB + kStages * kTileBytes;            // [kMaskStages][kChunks][256 queries] u32
+        static constexpr int kCommon = kMask + kMaskStages * kChunks * kBM * 4;   // [kMaskStages][kChunks] u32 (padded to 64 B)
+        static constexpr int kDirty = kCommon + ((kMaskStages * kChunks * 4 + 63) / 64) * 64;                        // [kMaskStages][32 lanes] u32: words a lane must clear
+        static constexpr int kScratch = kDirty + kMaskStages * 32 * 4;     // 8 warps x 32 floats
+        static constexpr int kBars = kScratch + 8 * 128;
+        static constexpr int kTotal = kBars + 512;
+        static_assert(kTotal <= 227 * 1024, "shared memory per CTA");
+    };
+};
 
 struct Cand {
     float s;
@@ -184,9 +207,6 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
 }
-// kind::tf32 instruction descriptor: D=F32, A=B=TF32, both K-major, N=96, M=128.
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-
 // ---------------------------------------------------------------------------------------------- sweep
 // Diagnostic timeline (CR_TC_DEBUG_MODE & 8): %globaltimer stamps of epilogue warp 0 of every unit, read back by
 // cr_debug_tc_timeline.  Slots: 0 entry, 1 setup done, 2 queries in TMEM, 3.. after tile 0, 15, 127, 1023, 4095, 8191, last, 10 exit (ns);
@@ -239,22 +259,14 @@ struct SweepParams {
     const int32_t* mask_col;
     const uint8_t* item_flags;
     uint8_t flag_exclude;
+    const uint32_t* bad_bits; // [n_tiles][kChunks] "never take" bit per item (flagged, or past the end of the table), precomputed
+                              // once per call when item flags are tested (item_bad_bits_kernel); nullptr: only the table tail
     Cand* buf;               // [S][n_q_pad][CAP]
     int* cnt;                // [S][n_q_pad]
     float* thr;              // [S][n_q_pad]
     float* dbg_scores;       // optional: raw TF32 scores of the first 256 x 96 block (probe)
     int seed_tiles;          // threshold seed phase: the first seed_tiles tiles are swept twice (see the kernel)
     int dbg_mode;            // timing experiments only (env CR_TC_DEBUG_MODE): 1 = skip TMEM loads, 2 = skip MMAs, 4 = interleave
-};
-
-struct SmemLayout {
-    static constexpr int kB = 0;                                       // kStages x 24 KB
-    static constexpr int kMask = kB + kStages * kTileBytes;            // [kMaskStages][kChunks][256 queries] u32
-    static constexpr int kCommon = kMask + kMaskStages * kChunks * kBM * 4;   // [kMaskStages][kChunks] u32 (padded to 64 B)
-    static constexpr int kDirty = kCommon + ((kMaskStages * kChunks * 4 + 63) / 64) * 64;                        // [kMaskStages][32 lanes] u32: words a lane must clear
-    static constexpr int kScratch = kDirty + kMaskStages * 32 * 4;     // 8 warps x 32 floats
-    static constexpr int kBars = kScratch + 8 * 128;
-    static constexpr int kTotal = kBars + 512;
 };
 
 // Rank-compact one query's candidate buffer to its best KSEL entries, sorted; returns the KSEL-th score.
@@ -333,8 +345,13 @@ __device__ __noinline__ float seed_threshold(const float* mine, int cap, int T0,
 // DBG = true compiles the probe / timing hooks (dbg_scores, dbg_mode, timeline) in; the production instantiation has none
 // of them: the hot loops of the four warp roles must stay inside the 32 KB L1.5 instruction cache (B300_MICROARCH.md) —
 // an earlier seed-phase variant that grew the kernel from 43 KB to 57 KB of SASS ran 14 % slower with identical hot loops.
-template <int KSEL, bool DBG>
+template <int D, int KSEL, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_i, const SweepParams p) {
+    using G = Geo<D>;
+    using SmemLayout = typename G::Smem;
+    constexpr int kD = G::kD, kBN = G::kBN, kAcc = G::kAcc, kStages = G::kStages, kChunks = G::kChunks, kChunkBytes = G::kChunkBytes,
+                  kTileBytes = G::kTileBytes, kTmemA = G::kTmemA, kTmemAcc = G::kTmemAcc;
+    constexpr uint32_t kIdesc = G::kIdesc;
     constexpr int CAP = KSEL + 32;
     constexpr int EPL = CAP / 32;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -392,8 +409,8 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
                 if (i >= kStages) mbar_wait(&empty[s], ((i / kStages) - 1) & 1);
                 mbar_expect_tx(&full[s], kTileBytes);
                 const int row = (tile_begin + (i < T0 ? i : i - T0)) * kBN;
-                tma_load_2d(sB + s * kTileBytes, &map_i, &full[s], 0, row);
-                tma_load_2d(sB + s * kTileBytes + kChunkBytes, &map_i, &full[s], 32, row);
+#pragma unroll
+                for (int bx = 0; bx < G::kBoxes; ++bx) tma_load_2d(sB + s * kTileBytes + bx * kChunkBytes, &map_i, &full[s], bx * 32, row);
             }
         }
     } else if (warp == 1) {
@@ -414,8 +431,8 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
                 const uint32_t d0 = tmem_base + kTmemAcc + a * (2 * kBN);
                 if (!DBG || !(p.dbg_mode & 2)) {
 #pragma unroll
-                    for (int m = 0; m < 16; ++m) {
-                        const int t = m >> 3, k = m & 7;
+                    for (int m = 0; m < 2 * (kD / 8); ++m) {
+                        const int t = m / (kD / 8), k = m % (kD / 8);
                         const uint32_t off16 = ((k >> 2) * kChunkBytes + (k & 3) * 32) >> 4;
                         const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(dlo + off16);
                         umma_tf32_ts(d0 + t * kBN, tmem_base + kTmemA + t * kD + k * 8, bdesc, kIdesc, k > 0 ? 1u : 0u);
@@ -440,7 +457,6 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
         for (int w = lane; w < kMaskStages * kChunks * kBM; w += 32) sMask[w] = 0;     // bitmaps start clean and are
         for (int m = 0; m < kMaskStages; ++m) sDirty[m * 32 + lane] = 0;               // cleaned lazily afterwards
         __syncwarp();
-        const bool plain = !p.item_gids && !p.item_flags;
         // Cursor setup: first train item at or after the first global id of this split.  The eight binary searches of a lane
         // advance together (eight independent loads per step instead of 8 x 7 dependent DRAM round trips, ~50 us per unit).
         int cur0[8];
@@ -476,6 +492,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
             for (int j = 0; j < 8; ++j) cur0[j] = (int)(lo8[j] - rlo[j]);
         }
         [[maybe_unused]] long long w_mempty = 0;
+        uint32_t bits_next = (p.bad_bits && lane < kChunks && n_local > 0) ? __ldg(p.bad_bits + (int64_t)tile_begin * kChunks + lane) : 0u;
         // two passes over the tiles when the seed phase is on: [0, T0) in seed mode, then the whole sweep from tile 0
         for (int pass = (T0 > 0 ? 0 : 1), i = 0; pass < 2; ++pass) {
             const int n_pass = pass == 0 ? T0 : n_local;
@@ -500,26 +517,25 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
                 uint32_t dirty = 0;
                 const int64_t pos0 = (int64_t)(tile_begin + k) * kBN;
                 int gid_lo = 0, gid_hi = 0;   // global id range covered by this tile: [gid_lo, gid_hi]
-                if (plain && pos0 + kBN <= p.n_items) {      // common case: contiguous ids, no flags, full tile
+                // Items nobody may take (flagged by the warm/cold setting, or past the end of the table): one word per
+                // 32-item chunk, the same for every query.  With item flags the words come from the per-call table
+                // (item_bad_bits_kernel) and are fetched ONE TILE AHEAD: r02 measured the former in-loop version — a flag byte
+                // per item loaded, balloted and shuffled by this warp inside every tile — at 0.54 of the unflagged sweep.
+                if (p.bad_bits) {
+                    if (lane < kChunks) sCommon[a * kChunks + lane] = bits_next;
+                    const int kn = (k + 1 < n_pass) ? k + 1 : 0;          // (the sweep pass restarts at tile 0 after the seed pass)
+                    if (lane < kChunks) bits_next = __ldg(p.bad_bits + (int64_t)(tile_begin + kn) * kChunks + lane);
+                } else if (lane < kChunks) {
+                    const int64_t left = p.n_items - (pos0 + lane * 32);
+                    sCommon[a * kChunks + lane] = left >= 32 ? 0u : (left <= 0 ? 0xffffffffu : ~((1u << (int)left) - 1u));
+                }
+                const int n_valid = (int)min((int64_t)kBN, p.n_items - pos0);
+                if (!p.item_gids) {           // contiguous ids
                     gid_lo = (int)(p.item_id_base + pos0);
-                    gid_hi = gid_lo + kBN - 1;
-                    if (lane < kChunks) sCommon[a * kChunks + lane] = 0;
-                } else {
-#pragma unroll
-                    for (int c = 0; c < kChunks; ++c) {
-                        const int64_t pos = pos0 + c * 32 + lane;
-                        bool bad = pos >= p.n_items;
-                        int gid = 0x7fffffff;
-                        if (!bad) {
-                            gid = p.item_gids ? __ldg(p.item_gids + pos) : (int)(p.item_id_base + pos);
-                            if (p.item_flags) bad = (__ldg(p.item_flags + gid) & p.flag_exclude) != 0;
-                        }
-                        const unsigned bits = __ballot_sync(CR_FULL_MASK, bad);
-                        if (lane == 0) sCommon[a * kChunks + c] = bits;
-                        if (c == 0) gid_lo = __shfl_sync(CR_FULL_MASK, gid, 0);
-                        const unsigned valid = __ballot_sync(CR_FULL_MASK, pos < p.n_items);
-                        if (valid) gid_hi = __shfl_sync(CR_FULL_MASK, gid, 31 - __clz(valid));
-                    }
+                    gid_hi = gid_lo + n_valid - 1;
+                } else {                      // compacted table: the ids of its first and last row in this tile
+                    gid_lo = __ldg(p.item_gids + pos0);
+                    gid_hi = __ldg(p.item_gids + pos0 + n_valid - 1);
                 }
                 __syncwarp();
 #pragma unroll
@@ -562,7 +578,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
         {   // A operand: this thread's query vector -> TMEM lane (quad*32 + lane), columns [t*64, t*64+64)
             uint32_t r[32];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < kD / 32; ++h) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -704,7 +720,7 @@ struct RescoreParams {
 
 // One warp per (query, split): exact fp32 scores of the candidates, top-K by (score desc, gid asc).
 // Candidates are never masked items (the sweep's bitmap dropped those).
-template <int EPL>
+template <int EPL, int kD>
 __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
     const int lane = threadIdx.x & 31;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -758,6 +774,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
 }
 
 // One thread per query, after the merge: prove the list or queue the query for the exact re-run.
+template <int kD>
 __global__ void verify_kernel(const RescoreParams p) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= p.n_q) return;
@@ -776,6 +793,7 @@ __global__ void verify_kernel(const RescoreParams p) {
     if (!(kth > thr + eps)) p.refine_list[atomicAdd(p.refine_count, 1)] = (int32_t)q;
 }
 
+template <int kD>
 __global__ void item_norm_max_kernel(const float4* __restrict__ item4, int64_t n_items, float* out) {
     float m = 0.f;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_items; r += (int64_t)gridDim.x * blockDim.x) {
@@ -791,6 +809,23 @@ __global__ void item_norm_max_kernel(const float4* __restrict__ item4, int64_t n
     if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));   // m >= 0: int order == float order
 }
 
+// One warp per (tile, 32-item chunk): bit l = item (tile * kBN + chunk * 32 + l) must never be taken — it carries the
+// excluded flag, or lies past the end of the table.
+__global__ void item_bad_bits_kernel(const uint8_t* __restrict__ item_flags, uint8_t flag_exclude, const int32_t* __restrict__ item_gids,
+                                     int64_t item_id_base, int64_t n_items, int64_t n_words, uint32_t* __restrict__ bits) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // word index = tile * kChunks + chunk = pos / 32
+    if (w >= n_words) return;
+    const int64_t pos = w * 32 + (threadIdx.x & 31);
+    bool bad = pos >= n_items;
+    if (!bad) {
+        const int64_t gid = item_gids ? (int64_t)__ldg(item_gids + pos) : item_id_base + pos;
+        bad = (__ldg(item_flags + gid) & flag_exclude) != 0;
+    }
+    const unsigned b = __ballot_sync(CR_FULL_MASK, bad);
+    if ((threadIdx.x & 31) == 0) bits[w] = b;
+}
+
+template <int kD>
 __global__ void gather_q_kernel(const float4* __restrict__ src, const int32_t* __restrict__ ids, int64_t n, float4* __restrict__ dst) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * (kD / 4)) return;
@@ -843,8 +878,8 @@ int get_encode_fn(EncodeTiledFn* out) {
     return CR_OK;
 }
 
-// rows x 64 fp32, row-major; box = 32 floats x kBN rows, SWIZZLE_128B; out-of-range rows read as zero
-int make_map(CUtensorMap* map, const float* base, int64_t rows) {
+// rows x kD fp32, row-major; box = 32 floats x kBN rows, SWIZZLE_128B; out-of-range rows read as zero
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int kD, int kBN) {
     EncodeTiledFn enc;
     int rc = get_encode_fn(&enc);
     if (rc != CR_OK) return rc;
@@ -861,10 +896,11 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows) {
 
 struct TcPlan {
     int ksel, cap, n_utiles, n_q_pad, n_tiles, S, tiles_per_split;
-    size_t off_q, off_buf, off_cnt, off_thr, off_norm, off_list, off_count, off_ps, off_pi, off_exact, exact_bytes, total;
+    size_t off_q, off_buf, off_cnt, off_thr, off_norm, off_list, off_count, off_ps, off_pi, off_bits, off_exact, exact_bytes, total;
 };
 
-TcPlan tc_plan(int64_t n_q, int64_t n_items, int K) {
+TcPlan tc_plan(int64_t n_q, int64_t n_items, int K, int kD) {
+    const int kBN = kD == 64 ? Geo<64>::kBN : Geo<128>::kBN;
     TcPlan P{};
     P.ksel = (K <= 24) ? 32 : 64;
     P.cap = P.ksel + 32;
@@ -896,6 +932,7 @@ TcPlan tc_plan(int64_t n_q, int64_t n_items, int K) {
     P.off_count = take(256);
     P.off_ps = take((size_t)P.S * n_q * K * 4);
     P.off_pi = take((size_t)P.S * n_q * K * 4);
+    P.off_bits = take((size_t)(P.n_tiles + 1) * (kBN / 32) * 4);      // "never take" words of the flag mask (tile-chunk granularity)
     P.exact_bytes = cr::refine_workspace_bytes(K);
     P.off_exact = take(P.exact_bytes);
     P.total = off;
@@ -906,21 +943,20 @@ TcPlan tc_plan(int64_t n_q, int64_t n_items, int K) {
 
 namespace cr {
 
+static inline bool tc_width(int d) { return d == 64 || d == 128; }
+
 size_t tc_workspace_bytes(int64_t n_q, int64_t n_items, int d, int K) {
-    if (d != kD || K > 52) return exact_workspace_bytes(n_q, n_items, K);
-    return tc_plan(n_q, n_items, K).total;
+    if (!tc_width(d) || K > 52) return exact_workspace_bytes(n_q, n_items, K);
+    return tc_plan(n_q, n_items, K, d).total;
 }
 
-int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_bytes, cudaStream_t st, float* dbg_scores) {
-    if (n_refined) CR_CUDA_TRY(cudaMemsetAsync(n_refined, 0, sizeof(int32_t), st));
-    if (j.d != kD || j.K > 52 || j.n_items == 0) {
-        // exact fp32 everywhere: a stricter result than TF32-checked asks for, never a weaker one
-        return launch_exact_scorer(j, ws, ws_bytes, st);
-    }
+template <int kD>
+static int launch_tc_scorer_d(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_bytes, cudaStream_t st, float* dbg_scores) {
+    using G = Geo<kD>;
     const int64_t n_q = j.n_q, n_items = j.n_items;
     const int K = j.K;
     if (n_q == 0) return CR_OK;
-    const TcPlan P = tc_plan(n_q, n_items, K);
+    const TcPlan P = tc_plan(n_q, n_items, K, kD);
     if (!ws || ws_bytes < P.total) return CR_ERR_WORKSPACE;
     if (!aligned16(ws)) return CR_ERR_ALIGN;
     char* base = (char*)ws;
@@ -939,13 +975,13 @@ int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_
     CR_CUDA_TRY(cudaMemsetAsync(rcount, 0, 256, st));
     {
         const int64_t total = n_q * (kD / 4);
-        gather_q_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float4*)j.user_tab, j.user_ids, n_q, (float4*)Q);
+        gather_q_kernel<kD><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float4*)j.user_tab, j.user_ids, n_q, (float4*)Q);
         CR_LAUNCH_CHECK("gather_q_kernel");
-        item_norm_max_kernel<<<148 * 4, 256, 0, st>>>((const float4*)j.item_tab, n_items, norm);
+        item_norm_max_kernel<kD><<<148 * 4, 256, 0, st>>>((const float4*)j.item_tab, n_items, norm);
         CR_LAUNCH_CHECK("item_norm_max_kernel");
     }
     CUtensorMap map_i;
-    int rc = make_map(&map_i, j.item_tab, n_items);
+    int rc = make_map(&map_i, j.item_tab, n_items, kD, G::kBN);
     if (rc != CR_OK) return rc;
 
     SweepParams sp{};
@@ -953,6 +989,15 @@ int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_
     sp.tiles_per_split = P.tiles_per_split; sp.n_tiles = P.n_tiles; sp.item_gids = j.item_gids; sp.item_id_base = j.item_id_base;
     sp.mask_rowptr = j.mask_rowptr; sp.mask_col = j.mask_col; sp.item_flags = flags;
     sp.flag_exclude = j.flag_exclude; sp.buf = buf; sp.cnt = cnt; sp.thr = thr; sp.dbg_scores = dbg_scores;
+    sp.bad_bits = nullptr;
+    if (flags) {
+        uint32_t* bits = (uint32_t*)(base + P.off_bits);
+        const int64_t n_words = (int64_t)P.n_tiles * G::kChunks;
+        item_bad_bits_kernel<<<(unsigned)((n_words * 32 + 255) / 256), 256, 0, st>>>(flags, j.flag_exclude, j.item_gids, j.item_id_base, n_items,
+                                                                                   n_words, bits);
+        CR_LAUNCH_CHECK("item_bad_bits_kernel");
+        sp.bad_bits = bits;
+    }
     sp.seed_tiles = 128;     // <= 2*CAP: the tile maxima live in the query's (still empty) candidate buffer
     if (const char* e = getenv("CR_TC_SEED_TILES")) sp.seed_tiles = min(128, max(0, atoi(e)));   // A/B knob (0 disables)
     {
@@ -962,10 +1007,11 @@ int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_
     const unsigned grid = (unsigned)(P.n_utiles * P.S);
     prof_start(PROF_SCORE_SWEEP, st);
     const bool dbg = sp.dbg_mode != 0 || dbg_scores != nullptr;
+    constexpr int kSmem = G::Smem::kTotal;
 #define CR_SWEEP(KS, DB)                                                                                                        \
     do {                                                                                                                        \
-        CR_CUDA_TRY(cudaFuncSetAttribute(score_sweep_tc_kernel<KS, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::kTotal)); \
-        score_sweep_tc_kernel<KS, DB><<<grid, kThreads, SmemLayout::kTotal, st>>>(map_i, sp);                                   \
+        CR_CUDA_TRY(cudaFuncSetAttribute(score_sweep_tc_kernel<kD, KS, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); \
+        score_sweep_tc_kernel<kD, KS, DB><<<grid, kThreads, kSmem, st>>>(map_i, sp);                                            \
     } while (0)
     if (P.ksel == 32) { if (dbg) CR_SWEEP(32, true); else CR_SWEEP(32, false); }
     else { if (dbg) CR_SWEEP(64, true); else CR_SWEEP(64, false); }
@@ -977,13 +1023,13 @@ int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_
                      part_s, part_i, j.out_score, rlist, rcount};
     const int64_t warps = n_q * P.S;
     const unsigned rgrid = (unsigned)((warps * 32 + 255) / 256);
-    if (P.cap == 64) rescore_kernel<2><<<rgrid, 256, 0, st>>>(rp); else rescore_kernel<3><<<rgrid, 256, 0, st>>>(rp);
+    if (P.cap == 64) rescore_kernel<2, kD><<<rgrid, 256, 0, st>>>(rp); else rescore_kernel<3, kD><<<rgrid, 256, 0, st>>>(rp);
     CR_LAUNCH_CHECK("rescore_kernel");
     if (P.S > 1) {
         rc = launch_merge(part_s, part_i, P.S, n_q, K, j.out_score, j.out_id, st, nullptr, 0, 0, -1, INT64_MAX);
         if (rc != CR_OK) return rc;
     }
-    verify_kernel<<<(unsigned)((n_q + 255) / 256), 256, 0, st>>>(rp);
+    verify_kernel<kD><<<(unsigned)((n_q + 255) / 256), 256, 0, st>>>(rp);
     CR_LAUNCH_CHECK("verify_kernel");
     // lists shorter than K (fewer than K unmasked items): show masked ids at -1e9 like the reference's top-K
     if (j.mask_rowptr || flags) {
@@ -999,6 +1045,16 @@ int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_
     if (rc != CR_OK) return rc;
     if (n_refined) CR_CUDA_TRY(cudaMemcpyAsync(n_refined, rcount, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     return CR_OK;
+}
+
+int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_bytes, cudaStream_t st, float* dbg_scores) {
+    if (n_refined) CR_CUDA_TRY(cudaMemsetAsync(n_refined, 0, sizeof(int32_t), st));
+    if (!tc_width(j.d) || j.K > 52 || j.n_items == 0) {
+        // exact fp32 everywhere: a stricter result than TF32-checked asks for, never a weaker one
+        return launch_exact_scorer(j, ws, ws_bytes, st);
+    }
+    return j.d == 64 ? launch_tc_scorer_d<64>(j, n_refined, ws, ws_bytes, st, dbg_scores)
+                     : launch_tc_scorer_d<128>(j, n_refined, ws, ws_bytes, st, dbg_scores);
 }
 
 int read_tc_timeline(unsigned long long* host_out, int n_units) {

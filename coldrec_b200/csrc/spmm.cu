@@ -38,6 +38,16 @@ constexpr int kThreads = 256;
 #ifndef CR_SPMM_LONG_U
 #define CR_SPMM_LONG_U 4      // gathers in flight per lane group in the warp-per-row / long-row-chunk kernels
 #endif
+// Work-balanced row ranges (graphs with a plan, bandwidth-bound geometry): warp w owns the consecutive rows whose cumulated
+// weight  rowptr[r] + kRowCost * r  falls in [w * kWarpWork, (w + 1) * kWarpWork) — about 2048 nonzero-equivalents, whether
+// that is 20 user rows of 100 nonzeros or 200 item rows of 2.  With a fixed 128 rows per warp a row block of a partitioned
+// bipartite graph (8 GPUs: 125k user rows + 1.26M item rows each) put half of its nonzeros into 977 warps of 12,800
+// nonzeros each — a 3.3 MB dependent gather stream per warp that set the duration of the whole launch (r02 probe: 2.4 ms
+// per layer and GPU against 1.2 ms of HBM time).  The table lives in the plan (built once per graph).
+constexpr int kRowCost = 8;
+constexpr int kWarpWork = 2048;
+inline int64_t balanced_warps(int64_t n_rows, int64_t nnz) { return (nnz + (int64_t)kRowCost * n_rows + kWarpWork - 1) / kWarpWork; }
+
 inline int long_row_of(int64_t nnz) { return nnz >= kSmallNnz ? kLongRow : kSmallLongRow; }
 inline int chunk_of(int64_t nnz) { return nnz >= kSmallNnz ? kChunk : kSmallChunk; }
 
@@ -61,8 +71,9 @@ struct Chunk {
 
 struct PlanLayout {
     int64_t max_long, max_chunks;
-    size_t off_long, off_chunks, off_partial, total;
+    size_t off_long, off_chunks, off_partial, off_warp_rows, total;     // total = up to the warp table; + warp_table_bytes()
 };
+inline size_t warp_table_bytes(int64_t n_rows, int64_t nnz) { return cr::align_up((size_t)(balanced_warps(n_rows, nnz) + 2) * sizeof(int32_t), 256); }
 
 PlanLayout plan_layout(int64_t nnz, int d) {
     PlanLayout L;
@@ -71,7 +82,8 @@ PlanLayout plan_layout(int64_t nnz, int d) {
     L.off_long = 256;
     L.off_chunks = cr::align_up(L.off_long + (size_t)L.max_long * sizeof(LongRow), 256);
     L.off_partial = cr::align_up(L.off_chunks + (size_t)L.max_chunks * sizeof(Chunk), 256);
-    L.total = cr::align_up(L.off_partial + (size_t)L.max_chunks * d * sizeof(float), 256);
+    L.off_warp_rows = cr::align_up(L.off_partial + (size_t)L.max_chunks * d * sizeof(float), 256);
+    L.total = L.off_warp_rows;      // offsets depend on (nnz, d) only: a plan built for n rows serves calls on its first m <= n rows
     return L;
 }
 
@@ -311,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
 spmm_rows_grouped_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
                          int64_t n_rows, const float4* __restrict__ X4, const Epi ep, int long_row, int kRowsPerWarp,
                          const PlanHeader* __restrict__ hdr, const Chunk* __restrict__ chunks, float4* __restrict__ partial4,
-                         int chunk_ctas) {
+                         int chunk_ctas, const int32_t* __restrict__ warp_rows, int64_t n_warps) {
     constexpr int RPW = 32 / LPR;     // rows in flight per warp; U = gathers issued back to back per group
     constexpr int d4 = LPR * NV;
     static_assert(LPR % U == 0, "a group's LPR column ids are consumed U at a time");
@@ -328,14 +340,20 @@ spmm_rows_grouped_kernel(const int64_t* __restrict__ rowptr, const int32_t* __re
         walk_chunks<LPR, NV, HAS_VAL>(hdr, chunks, col, val, X4, partial4, chunk_ctas);
         return;
     }
-    const int64_t row0 = (((int64_t)(blockIdx.x - chunk_ctas) * kThreads + threadIdx.x) >> 5) * kRowsPerWarp;
-    if (row0 >= n_rows) return;
-    const int64_t row_end = min(n_rows, row0 + kRowsPerWarp);
+    const int64_t wid = ((int64_t)(blockIdx.x - chunk_ctas) * kThreads + threadIdx.x) >> 5;
+    int64_t row0 = wid * kRowsPerWarp, row_end = row0 + kRowsPerWarp;
+    if (warp_rows) {                  // work-balanced ranges from the plan
+        if (wid >= n_warps) return;
+        row0 = __ldg(warp_rows + wid);
+        row_end = __ldg(warp_rows + wid + 1);
+    }
+    row_end = min(n_rows, row_end);
+    if (row0 >= row_end) return;
     for (int64_t r32 = row0; r32 < row_end; r32 += 32) {
         const int64_t rr = r32 + lane;
         int64_t lo = __ldg(rowptr + min(rr, n_rows));
         int64_t hi = __ldg(rowptr + min(rr + 1, n_rows));
-        const bool skip_row = (rr >= n_rows) || (hi - lo > long_row);   // long rows belong to the split path
+        const bool skip_row = (rr >= row_end) || (hi - lo > long_row);  // long rows belong to the split path, later rows to the next warp
         if (skip_row) hi = lo;
         [[maybe_unused]] const unsigned skip32 = STAGED ? __ballot_sync(CR_FULL_MASK, skip_row) : 0u;
         int c_nb = 0;
@@ -438,6 +456,19 @@ __global__ void spmm_plan_kernel(const int64_t* __restrict__ rowptr, int64_t n_r
     }
 }
 
+// warp_rows[w] = first row r with rowptr[r] + kRowCost * r >= w * kWarpWork (w = 0 .. n_warps; the last entry is n_rows)
+__global__ void spmm_warp_rows_kernel(const int64_t* __restrict__ rowptr, int64_t n_rows, int64_t n_warps, int32_t* __restrict__ warp_rows) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w > n_warps) return;
+    const int64_t target = w * kWarpWork;
+    int64_t lo = 0, hi = n_rows;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (rowptr[mid] + (int64_t)kRowCost * mid < target) lo = mid + 1; else hi = mid;
+    }
+    warp_rows[w] = (int32_t)(w == n_warps ? n_rows : lo);
+}
+
 template <int LPR, int NV, bool HAS_VAL, bool BOUNDS>
 __global__ void __launch_bounds__(kThreads)
 spmm_long_chunks_kernel(const PlanHeader* __restrict__ hdr, const Chunk* __restrict__ chunks,
@@ -509,6 +540,7 @@ struct SpmmArgs {
     PlanHeader* hdr; LongRow* long_rows; Chunk* chunks; float4* partial4;
     cudaStream_t stream;
     int long_row;
+    const int32_t* warp_rows;      // work-balanced row ranges of the plan (nullptr: fixed rows per warp)
 };
 
 template <int LPR, int NV, bool BOUNDS, int GLPR = 0, int GNV = 0, int GU = 4, int GMINB = 3, int SLPR = GLPR, int SNV = GNV>
@@ -523,7 +555,9 @@ int launch_spmm(const SpmmArgs& a) {
             // rows per warp so that the grid still covers the SMs (CiteULike-shaped, 22.5k rows: 22 -> 88 CTAs)
             const bool big = a.n_rows >= (int64_t)148 * 24 * 128 || getenv("CR_SPMM_FORCE_BIG");   // (test knob: wide geometry on small graphs)
             const int rows_per_warp = big ? 128 : 32;
-            const int64_t warps = (a.n_rows + rows_per_warp - 1) / rows_per_warp;
+            const int32_t* warp_rows = (big && !getenv("CR_SPMM_FIXED_ROWS")) ? a.warp_rows : nullptr;     // (A/B knob)
+            const int64_t n_bal = balanced_warps(a.n_rows, a.nnz);
+            const int64_t warps = warp_rows ? n_bal : (a.n_rows + rows_per_warp - 1) / rows_per_warp;
             // long-row chunks ride in the first CTAs of the same launch (the plan lives on the device: size by its upper bound)
             const int64_t max_chunks = a.hdr ? a.nnz / chunk_of(a.nnz) + a.nnz / (long_row_of(a.nnz) + 1) + 2 : 0;
             const int chunk_ctas = (int)min((int64_t)148 * GMINB, (max_chunks * 32 + kThreads - 1) / kThreads);
@@ -538,7 +572,8 @@ int launch_spmm(const SpmmArgs& a) {
             const bool staged = a.ep.peers && !a.ep.mc4 && GLPR * GNV <= 16 && !getenv("CR_SPMM_PEER_ST");
 #define CR_GROUPED_(L_, N_, V_, U_, B_, S_)                                                                                     \
     spmm_rows_grouped_kernel<L_, N_, V_, U_, B_, S_><<<gblocks, kThreads, 0, a.stream>>>(                                       \
-        a.rowptr, a.col, a.val, a.n_rows, a.X4, a.ep, long_row, rows_per_warp, a.hdr, a.chunks, a.partial4, chunk_ctas)
+        a.rowptr, a.col, a.val, a.n_rows, a.X4, a.ep, long_row, rows_per_warp, a.hdr, a.chunks, a.partial4, chunk_ctas,     \
+        warp_rows, n_bal)
 #define CR_GROUPED(L_, N_, V_, U_, B_)                                                                                          \
     do {                                                                                                                        \
         if constexpr ((L_) * (N_) <= 16) { if (staged) CR_GROUPED_(L_, N_, V_, U_, B_, true); else CR_GROUPED_(L_, N_, V_, U_, B_, false); } \
@@ -584,16 +619,15 @@ int launch_spmm(const SpmmArgs& a) {
 extern "C" {
 
 size_t cr_spmm_plan_bytes(int64_t n_rows, int64_t nnz, int d) {
-    (void)n_rows;
-    if (nnz < 0 || d <= 0) return 0;
-    return plan_layout(nnz, d).total;
+    if (nnz < 0 || d <= 0 || n_rows < 0) return 0;
+    return plan_layout(nnz, d).total + warp_table_bytes(n_rows, nnz);
 }
 
 int cr_spmm_plan(const int64_t* rowptr, int64_t n_rows, int64_t nnz, int d, void* plan, size_t plan_bytes, void* stream) {
     if (!rowptr || !plan || n_rows < 0 || nnz < 0 || d <= 0) return CR_ERR_ARG;
     if (n_rows > 0x7fffffffLL) return CR_ERR_UNSUPPORTED;
     const PlanLayout L = plan_layout(nnz, d);
-    if (plan_bytes < L.total) return CR_ERR_WORKSPACE;
+    if (plan_bytes < L.total + warp_table_bytes(n_rows, nnz)) return CR_ERR_WORKSPACE;
     if (L.max_chunks > 0x7fffffffLL) return CR_ERR_UNSUPPORTED;
     int rc = cr::require_device();
     if (rc != CR_OK) return rc;
@@ -606,6 +640,9 @@ int cr_spmm_plan(const int64_t* rowptr, int64_t n_rows, int64_t nnz, int d, void
                                                  (Chunk*)(base + L.off_chunks), (int)L.max_long, (int)L.max_chunks, long_row_of(nnz),
                                                  chunk_of(nnz));
         CR_LAUNCH_CHECK("spmm_plan_kernel");
+        const int64_t n_warps = balanced_warps(n_rows, nnz);
+        spmm_warp_rows_kernel<<<(unsigned)((n_warps + 1 + 255) / 256), 256, 0, st>>>(rowptr, n_rows, n_warps, (int32_t*)(base + L.off_warp_rows));
+        CR_LAUNCH_CHECK("spmm_warp_rows_kernel");
     }
     return CR_OK;
 }
@@ -627,10 +664,12 @@ static int spmm_entry(const int64_t* rowptr, const int32_t* col, const float* va
                Epi{(float4*)Y, (const float4*)(acc_in ? acc_in : acc), (float4*)acc, acc_beta, acc_div, (float4* const*)peers,
                    peers ? n_peers : 0, peer_row_offset * (d / 4), peer_row_split * (d / 4), peer_row_offset_hi * (d / 4), bcast_acc, peers ? peer_need : nullptr,
                    peers ? (float4*)mc_table : nullptr, (peers && n_peers < 32) ? (1u << n_peers) - 1u : 0xffffffffu},
-               nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream, long_row_of(nnz)};
+               nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream, long_row_of(nnz), nullptr};
     if (plan) {
         const PlanLayout L = plan_layout(nnz, d);
-        if (plan_bytes < L.total) return CR_ERR_WORKSPACE;
+        // the plan may have been built for more rows than this call covers (empty padding rows at the end of a partition)
+        if (plan_bytes < L.total + warp_table_bytes(n_rows, nnz)) return CR_ERR_WORKSPACE;
+        a.warp_rows = (const int32_t*)((char*)plan + L.off_warp_rows);
         char* base = (char*)plan;
         a.hdr = (PlanHeader*)base;
         a.long_rows = (LongRow*)(base + L.off_long);

@@ -14,6 +14,7 @@ import torch
 from . import _lib
 
 __all__ = ["spmm_plan", "spmm", "spmm_bcast", "score_topk", "topk_merge", "fill_masked", "gather_rows", "rank_metrics", "linear_act", "bn_fold",
+           "SplitTable", "split_tf32", "linear_act_tc",
            "heater_blend", "bpr_fwd_bwd", "adam_step", "sample_pairwise", "SCORE_EXACT_F32", "SCORE_TF32_CHECKED"]
 
 SCORE_EXACT_F32 = _lib.SCORE_EXACT_F32
@@ -324,6 +325,82 @@ def linear_act(X1, W, bias=None, *, X2=None, xrow=None, scale=None, shift=None, 
                                    out.stride(0), _ptr(yrow), _stream(dev))
     _lib.check(rc, "cr_linear_act_f32")
     return out
+
+
+class SplitTable:
+    """A table as the tensor-core tower kernel consumes it: ``x == hi + lo`` exactly, ``hi`` representable in TF32.  Both
+    halves are (rows, ld) fp32 with ld = width rounded up to a multiple of 4 (zero columns): a legal TMA row stride."""
+    __slots__ = ("hi", "lo", "width")
+
+    def __init__(self, hi: torch.Tensor, lo: torch.Tensor, width: int):
+        self.hi, self.lo, self.width = hi, lo, int(width)
+
+    @property
+    def rows(self) -> int:
+        return self.hi.shape[0]
+
+
+def split_tf32(x: torch.Tensor) -> SplitTable:
+    """hi = round-to-nearest-TF32(x), lo = x - hi for a (rows, cols) fp32 table with unit inner stride (``cr_split_tf32``).
+    Do it once for constant tables (item content) and keep the result."""
+    lib = _lib.load()
+    x = _req(x, torch.float32, "x", contiguous=False)
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be 2-D with unit inner stride")
+    rows, cols = x.shape
+    ld = (cols + 3) // 4 * 4
+    hi = torch.empty((rows, ld), dtype=torch.float32, device=x.device)
+    lo = torch.empty((rows, ld), dtype=torch.float32, device=x.device)
+    if rows:
+        with torch.cuda.device(x.device):
+            rc = lib.cr_split_tf32(_ptr(x), max(x.stride(0), cols), rows, cols, _ptr(hi), _ptr(lo), ld, _stream(x.device))
+        _lib.check(rc, "cr_split_tf32")
+    return SplitTable(hi, lo, cols)
+
+
+def linear_act_tc(X1: SplitTable, W: SplitTable, bias=None, *, X2: Optional[SplitTable] = None, scale=None, shift=None, act=None,
+                  out=None, yrow=None, want_split: bool = False, want_plain: bool = True):
+    """``linear_act`` on the tensor cores at fp32 accuracy (``cr_linear_act_tc_f32``: tcgen05 kind::tf32, hi.hi + lo.hi + hi.lo).
+    X1 / X2 / W are ``SplitTable``s (W = split of the nn.Linear weight [n_out, X1.width + X2.width]).  Returns
+    (out | None, SplitTable of the output | None) — with ``want_split`` the output is emitted already split for the next
+    layer.  Rows are contiguous (no gather); ``yrow`` scatters the rows of ``out`` (GAR.py:44-46)."""
+    lib = _lib.load()
+    tabs = [X1.hi, X1.lo, W.hi, W.lo] + ([X2.hi, X2.lo] if X2 is not None else [])
+    for t in tabs:
+        _req(t, torch.float32, "split table")
+    bias = _req(bias, torch.float32, "bias", optional=True)
+    scale = _req(scale, torch.float32, "scale", optional=True)
+    shift = _req(shift, torch.float32, "shift", optional=True)
+    yrow = _req(yrow, torch.int32, "yrow", optional=True)
+    dev = _same_device(*tabs, bias, scale, shift, yrow, out)
+    n_rows, n_out = X1.rows, W.rows
+    d1, d2 = X1.width, (0 if X2 is None else X2.width)
+    if W.width != d1 + d2:
+        raise ValueError(f"W has {W.width} columns, inputs give k={d1 + d2}")
+    if X2 is not None and X2.rows != n_rows:
+        raise ValueError("X1 and X2 differ in rows")
+    if act not in _ACTS:
+        raise ValueError(f"unknown activation {act!r}")
+    if out is None and want_plain:
+        if yrow is not None:
+            raise ValueError("a scatter (yrow) needs an existing `out` table")
+        out = torch.empty((n_rows, n_out), dtype=torch.float32, device=dev)
+    if out is not None:
+        _req(out, torch.float32, "out", contiguous=False)
+    sp = None
+    if want_split:
+        ldh = (n_out + 3) // 4 * 4
+        sp = SplitTable(torch.empty((n_rows, ldh), dtype=torch.float32, device=dev), torch.empty((n_rows, ldh), dtype=torch.float32, device=dev), n_out)
+    if n_rows == 0:
+        return out, sp
+    with torch.cuda.device(dev):
+        rc = lib.cr_linear_act_tc_f32(_ptr(X1.hi), _ptr(X1.lo), X1.hi.stride(0), d1, _ptr(None if X2 is None else X2.hi),
+                                      _ptr(None if X2 is None else X2.lo), 0 if X2 is None else X2.hi.stride(0), d2, n_rows,
+                                      _ptr(W.hi), _ptr(W.lo), W.hi.stride(0), _ptr(bias), _ptr(scale), _ptr(shift), n_out, _ACTS[act],
+                                      _ptr(out), 0 if out is None else out.stride(0), _ptr(yrow), _ptr(None if sp is None else sp.hi),
+                                      _ptr(None if sp is None else sp.lo), 0 if sp is None else sp.hi.stride(0), _stream(dev))
+    _lib.check(rc, "cr_linear_act_tc_f32")
+    return out, sp
 
 
 def bn_fold(gamma, beta, mean, var, eps: float):

@@ -123,6 +123,7 @@ class FullRankScorer:
     def __init__(self, K: int, precision: int = ops.SCORE_TF32_CHECKED):
         self.K, self.precision = int(K), precision
         self._gid_cache = {}                         # (flags identity, group, excl) -> kept item ids; never table contents
+        self._remap_cache = {}                       # (plan identity, selection) -> train-mask CSR in rows of the compacted table
         self.n_refined: List[torch.Tensor] = []      # device counters of the last topk() call
 
     def _kept_ids(self, item_flags: torch.Tensor, keep_mask_fn, key) -> torch.Tensor:
@@ -140,6 +141,29 @@ class FullRankScorer:
             self._gid_cache[ck] = hit
         return hit[1]
 
+    def _mask_in_rows_of(self, plan: EvalPlan, gids: torch.Tensor, key):
+        """The plan's train-mask CSR re-expressed in ROW NUMBERS of a compacted item table (``gids`` = the kept item ids,
+        ascending): entries whose item was compacted away are dropped, the others become their row number, order kept.
+        The sweep then sees a contiguous catalogue 0 .. len(gids)-1 — its fast mask path — instead of locating every train
+        item inside every tile of an id list (r02: 0.40-0.45 of the tensor peak on that path against 0.99); the ranked row
+        numbers are mapped back through ``gids`` afterwards (row order = id order, so ties break the same way).
+        Memoised per (plan, selection): plans are memoised per eval set, the selection is a function of the flag bytes."""
+        ck = (id(plan), key)
+        hit = self._remap_cache.get(ck)
+        if hit is None or hit[0] is not plan:
+            col = plan.mask_col
+            pos = torch.searchsorted(gids, col)
+            valid = gids[pos.clamp(max=gids.numel() - 1)] == col
+            lens = plan.mask_rowptr[1:] - plan.mask_rowptr[:-1]
+            rowid = torch.repeat_interleave(torch.arange(plan.n_q, device=col.device), lens)
+            rowptr = torch.zeros(plan.n_q + 1, dtype=torch.int64, device=col.device)
+            rowptr[1:] = torch.cumsum(torch.bincount(rowid[valid], minlength=plan.n_q), 0)
+            if len(self._remap_cache) >= 16:
+                self._remap_cache.clear()
+            hit = (plan, rowptr, pos[valid].to(torch.int32).contiguous())
+            self._remap_cache[ck] = hit
+        return hit[1], hit[2]
+
     def topk(self, tables, plan: EvalPlan, item_flags: Optional[torch.Tensor] = None):
         K, excl = self.K, plan.flag_exclude
         if excl and item_flags is None:
@@ -150,25 +174,35 @@ class FullRankScorer:
         lists, compacted = [], False
         self.n_refined = []
         for user_tab, item_tab, group in tables:
-            tab, gids, kflags, kexcl = item_tab, None, None, 0
+            tab, gids, kflags, kexcl, sel = item_tab, None, None, 0, None
             if group is not None:
                 if item_flags is None:
                     raise ValueError("item groups need item_flags")
                 def keep(group=group):
                     k = (item_flags & (FLAG_WARM | FLAG_COLD)) == 0 if group == GROUP_UNFLAGGED else (item_flags & group) != 0
                     return k & ((item_flags & excl) == 0) if excl else k
-                gids = self._kept_ids(item_flags, keep, (group, excl))
+                sel = (group, excl)
+                gids = self._kept_ids(item_flags, keep, sel)
                 tab, compacted = ops.gather_rows(item_tab, gids), True
             elif excl:
-                gids = self._kept_ids(item_flags, lambda: (item_flags & excl) == 0, (0, excl))
+                sel = (0, excl)
+                gids = self._kept_ids(item_flags, lambda: (item_flags & excl) == 0, sel)
                 if gids.numel() < 0.9 * item_tab.shape[0]:         # skipping flagged items outright is cheaper
                     tab, compacted = ops.gather_rows(item_tab, gids), True
                 else:                                              # few items flagged: mask them inside the kernel instead
                     gids, kflags, kexcl = None, item_flags, excl
             if tab.shape[0] == 0:
                 continue
-            s, i, nref = ops.score_topk(user_tab, tab, K, user_ids=plan.user_ids, item_gids=gids, mask_rowptr=plan.mask_rowptr,
-                                        mask_col=plan.mask_col, item_flags=kflags, flag_exclude=kexcl, precision=self.precision)
+            if gids is not None:       # compacted table: sweep it as a contiguous catalogue of row numbers, map the rows back to ids
+                if plan.mask_col.numel():
+                    mrp, mcol = self._mask_in_rows_of(plan, gids, (item_flags.data_ptr(), item_flags._version, sel))
+                else:
+                    mrp, mcol = plan.mask_rowptr, plan.mask_col
+                s, i, nref = ops.score_topk(user_tab, tab, K, user_ids=plan.user_ids, mask_rowptr=mrp, mask_col=mcol, precision=self.precision)
+                i = torch.where(i >= 0, gids[i.clamp(min=0).long()], i)
+            else:
+                s, i, nref = ops.score_topk(user_tab, tab, K, user_ids=plan.user_ids, mask_rowptr=plan.mask_rowptr,
+                                            mask_col=plan.mask_col, item_flags=kflags, flag_exclude=kexcl, precision=self.precision)
             self.n_refined.append(nref)
             lists.append((s, i))
         if not lists:

@@ -188,6 +188,20 @@ CR_API int cr_rank_metrics(const int32_t *topk_id, int64_t n_q, int K, const int
 CR_API int cr_linear_act_f32(const float *X1, int64_t ld1, int d1, const float *X2, int64_t ld2, int d2, const int32_t *xrow,
                       int64_t n_rows, const float *W, const float *bias, const float *scale, const float *shift,
                       int n_out, int act, float *Y, int64_t ldy, const int32_t *yrow, void *stream);
+/* The same layer on the tensor cores (tcgen05, kind::tf32) at fp32 accuracy ("3xTF32"): every operand comes split as
+ * x = hi + lo with hi exactly representable in TF32 (cr_split_tf32), and hi.hi + lo.hi + hi.lo is accumulated in fp32.
+ * Rows are contiguous (no xrow gather); X1/X2/W tables need 16-byte aligned bases and row strides (ld % 4 == 0);
+ * n_out <= 256.  Outputs: Y (nullable, scattered through yrow if given) and/or the split (Yhi, Ylo) of the same values
+ * with row stride ldh >= n_out (columns [n_out, ldh) are zeroed) — the next layer's input without a split pass.
+ * Same replaced reference lines as cr_linear_act_f32. */
+CR_API int cr_linear_act_tc_f32(const float *X1hi, const float *X1lo, int64_t ld1, int d1, const float *X2hi, const float *X2lo,
+                         int64_t ld2, int d2, int64_t n_rows, const float *Whi, const float *Wlo, int64_t ldw,
+                         const float *bias, const float *scale, const float *shift, int n_out, int act, float *Y,
+                         int64_t ldy, const int32_t *yrow, float *Yhi, float *Ylo, int64_t ldh, void *stream);
+/* hi = round-to-nearest-TF32(src), lo = src - hi, for a rows x cols table (row stride ld_src); destination row stride
+ * ld_dst >= cols, columns [cols, ld_dst) zeroed (pads a 2,738-wide content table to a TMA-legal stride). */
+CR_API int cr_split_tf32(const float *src, int64_t ld_src, int64_t rows, int cols, float *hi, float *lo, int64_t ld_dst,
+                  void *stream);
 /* scale = gamma / sqrt(var + eps); shift = beta - mean * scale   (eval BatchNorm1d, DropoutNet.py:226-230) */
 CR_API int cr_bn_fold_f32(const float *gamma, const float *beta, const float *mean, const float *var, float eps, int n,
                    float *scale, float *shift, void *stream);

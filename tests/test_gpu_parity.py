@@ -328,16 +328,18 @@ def test_score_topk_vs_oracle_synthetic(shape, precision):
         assert (np.diff(si, axis=1) <= 0).all(), "scores must be sorted descending"
 
 
+@pytest.mark.parametrize("d", [64, 128])
 @pytest.mark.parametrize("seed_tiles", [4, 16, 128])
 @pytest.mark.parametrize("K", [20, 50])
-def test_score_topk_seed_phase_vs_oracle(seed_tiles, K, monkeypatch):
+def test_score_topk_seed_phase_vs_oracle(seed_tiles, K, d, monkeypatch):
     """The threshold seed phase of the tcgen05 scorer (first T0 tiles swept twice).  It switches on when a unit sweeps at
     least 8*T0 tiles; CR_TC_SEED_TILES (read per call) lowers T0 so that oracle-sized cases exercise it: masked and flagged
-    items inside the seed tiles, 2 % duplicated item rows (exact ties at the seed threshold), K = 50 (KSEL = 64)."""
+    items inside the seed tiles, 2 % duplicated item rows (exact ties at the seed threshold), K = 50 (KSEL = 64).  d = 128 is
+    the VBPR / AMR instantiation of the same kernel (64-item tiles, four TMA boxes per tile, 2 x 16 MMAs)."""
     from coldrec_b200 import ops
     monkeypatch.setenv("CR_TC_SEED_TILES", str(seed_tiles))
     n_users, n_items, n_q = 2000, 110000 if seed_tiles == 128 else 30000, 1200
-    U, I, uids, rowptr, col, flags = _synthetic_scoring_case(4242 + seed_tiles + K, n_users, n_items, n_q, 64, 300, 0.02)
+    U, I, uids, rowptr, col, flags = _synthetic_scoring_case(4242 + seed_tiles + K, n_users, n_items, n_q, d, 300, 0.02)
     col_head = np.sort(np.random.default_rng(K).choice(400, 60, replace=False)).astype(np.int32)   # masks concentrated in the seed tiles
     rows = [np.union1d(col[rowptr[j]:rowptr[j + 1]], col_head).astype(np.int32) for j in range(n_q)]
     rowptr = np.zeros(n_q + 1, dtype=np.int64); np.cumsum([len(r) for r in rows], out=rowptr[1:])
@@ -424,6 +426,43 @@ def test_towers_vs_reference_golden():
 
 
 # ---------------------------------------------------------------------------------------------- tcgen05 probe
+@pytest.mark.parametrize("shape", [(300, 64, 0, 200), (1000, 64, 2738, 200), (257, 200, 0, 100), (129, 100, 0, 64), (640, 2738, 0, 5),
+                                   (77, 24, 0, 128), (513, 2738, 0, 205), (128, 36, 300, 256), (1, 8, 0, 16)])
+def test_tower_layer_tc_3xtf32_matches_fp64(shape):
+    """cr_linear_act_tc_f32 (tcgen05, hi.hi + lo.hi + hi.lo) against an fp64 evaluation of the same layer: widths that are not
+    multiples of the 32-float K chunk or of the 16-column MMA N, the two-segment K loop ([V | content]), ragged last row
+    tile, folded BatchNorm + tanh, the split outputs handed to the next layer, and the row scatter."""
+    from coldrec_b200 import ops
+    n, d1, d2, n_out = shape
+    rng = np.random.default_rng(sum(shape))
+    X1 = rng.standard_normal((n, d1)).astype(np.float32)
+    X2 = (rng.standard_normal((n, d2)) * (rng.random((n, d2)) < 0.05)).astype(np.float32) if d2 else None
+    W = (rng.standard_normal((n_out, d1 + d2)) * 0.05).astype(np.float32)
+    b = rng.standard_normal(n_out).astype(np.float32) * 0.1
+    sc = (rng.random(n_out) + 0.5).astype(np.float32)
+    sh = (rng.standard_normal(n_out) * 0.1).astype(np.float32)
+    Xcat = np.concatenate([X1, X2], 1).astype(np.float64) if d2 else X1.astype(np.float64)
+    pre = (Xcat @ W.astype(np.float64).T + b) * sc + sh
+    ref = np.tanh(pre)
+    y, sp = ops.linear_act_tc(ops.split_tf32(cu(X1)), ops.split_tf32(cu(W)), cu(b), X2=ops.split_tf32(cu(X2)) if d2 else None,
+                              scale=cu(sc), shift=cu(sh), act="tanh", want_split=True)
+    assert_normwise(y, ref.astype(np.float32), tol=2e-6)
+    # the split output is the same value, exactly: hi + lo == y, hi is TF32-representable, padding columns are zero
+    hi, lo = sp.hi.cpu().numpy(), sp.lo.cpu().numpy()
+    assert np.array_equal((hi.astype(np.float64) + lo)[:, :n_out].astype(np.float32), y.cpu().numpy())
+    assert (hi.view(np.uint32) & 0x1FFF).max() == 0 and not hi[:, n_out:].any() and not lo[:, n_out:].any()
+    # no epilogue, scattered rows
+    perm = rng.permutation(n + 3)[:n].astype(np.int32)
+    out = torch.full((n + 3, n_out), 7.0, device=DEV)
+    ops.linear_act_tc(ops.split_tf32(cu(X1)), ops.split_tf32(cu(W)), None, X2=ops.split_tf32(cu(X2)) if d2 else None, out=out, yrow=cu(perm))
+    want = np.full((n + 3, n_out), 7.0)
+    want[perm] = Xcat @ W.astype(np.float64).T
+    assert_normwise(out, want.astype(np.float32), tol=2e-6)
+    # and the SIMT kernel agrees to the parity tolerance
+    y2 = ops.linear_act(cu(X1), cu(W), cu(b), X2=cu(X2) if d2 else None, scale=cu(sc), shift=cu(sh), act="tanh")
+    assert_normwise(y2, ref.astype(np.float32), tol=1e-5)
+
+
 def test_tc_raw_scores_are_tf32_products():
     """The tensor-core sweep must see <q, x> with at most TF32 operand error: |err| <= 2^-9 |q||x|."""
     from coldrec_b200 import ops

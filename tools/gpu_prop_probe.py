@@ -35,10 +35,60 @@ PG.local.plan(D); PG.enable_p2p(D)
 ru, ri = cr.propagate(G, E0[:n_users].contiguous(), E0[n_users:].contiguous(), L)
 ref = torch.cat([ru, ri]); del ru, ri
 scale = ref.abs().max().item()
-variants = [("tma full", {}, {}), ("st full", {"CR_SPMM_PEER_ST": "1"}, {}), ("tma users", {}, {"replicate_result": (0,)}),
-            ("tma dense", {}, {"sparse": False}), ("tma multicast", {}, {"multicast": True})]
-for name, env, kw in variants:
+# ---- what the fabric itself does with this exchange: NCCL all-gather, copy-engine pushes, the kernel's push path with no SpMM work
+def timed(fn, iters=8):
+    for _ in range(2): fn()
+    dist.barrier(device_ids=[dev.index]); torch.cuda.synchronize()
+    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters): fn()
+    b_.record(); torch.cuda.synchronize()
+    t_ = torch.tensor([a.elapsed_time(b_) / iters], dtype=torch.float64, device=dev)
+    dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+    return round(float(t_.item()), 3)
+from coldrec_b200 import ops
+nl, rp_ = PG.n_local, PG.rows_pad
+y = torch.randn(rp_, D, device=dev)
+ag_out = torch.empty(world * rp_, D, device=dev)
+fabric = {"bytes_per_gpu_egress": nl * D * 4 * (world - 1)}
+fabric["nccl_all_gather_ms"] = timed(lambda: dist.all_gather_into_tensor(ag_out, y))
+try:
+    h = PG._xhdl[2]
+    peers = [h.get_buffer(p, (world * rp_, D), torch.float32) for p in range(world)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    def ce_push():
+        cur = torch.cuda.current_stream()
+        for k in range(1, world):
+            p = (rank + k) % world
+            streams[p].wait_stream(cur)
+            with torch.cuda.stream(streams[p]):
+                peers[p][rank * rp_:rank * rp_ + nl].copy_(y[:nl], non_blocking=True)
+        for k in range(1, world):
+            cur.wait_stream(streams[(rank + k) % world])
+        h.barrier()
+    fabric["copy_engine_push_ms"] = timed(ce_push)
+except Exception as ex:
+    fabric["copy_engine_push_ms"] = f"{type(ex).__name__}: {str(ex)[:100]}"
+zrp = torch.zeros(nl + 1, dtype=torch.int64, device=dev); zc = torch.zeros(1, dtype=torch.int32, device=dev)[:0]
+acc0 = torch.zeros(rp_, D, device=dev)
+def kernel_push():
+    ops.spmm_bcast(zrp, zc, None, E0, PG._xhdl[2].buffer_ptrs_dev, world, rank * rp_, acc=acc0[:nl], acc_beta=1.0, acc_div=1.0,
+                   plan=None, bcast_acc=True)
+    PG._xhdl[2].barrier()
+for nm, env in (("kernel_push_tma_ms", {}), ("kernel_push_st_ms", {"CR_SPMM_PEER_ST": "1"})):
     os.environ.pop("CR_SPMM_PEER_ST", None); os.environ.update(env)
+    try:
+        fabric[nm] = timed(kernel_push)
+    except Exception as ex:
+        fabric[nm] = f"{type(ex).__name__}: {str(ex)[:100]}"
+os.environ.pop("CR_SPMM_PEER_ST", None)
+if rank == 0:
+    print(json.dumps({"fabric": fabric, "world": world, "what": "dense exchange of one layer (every local row to every peer), no SpMM work"}), flush=True)
+
+variants = [("tma full", {}, {}), ("tma full, fixed 128 rows per warp", {"CR_SPMM_FIXED_ROWS": "1"}, {}), ("st full", {"CR_SPMM_PEER_ST": "1"}, {}),
+            ("tma users", {}, {"replicate_result": (0,)}), ("tma dense", {}, {"sparse": False})]
+for name, env, kw in variants:
+    os.environ.pop("CR_SPMM_PEER_ST", None); os.environ.pop("CR_SPMM_FIXED_ROWS", None); os.environ.update(env)
     run = lambda ev=None: PG.propagate_p2p(E0, L, copy=False, layer_events=ev, **kw)
     for _ in range(3): res = run()
     if "replicate_result" in kw:

@@ -30,10 +30,10 @@ def ref_topk(U, I, uids, rowptr, col, K, flags=None, excl=0):
     return torch.topk(S, K, dim=1)
 
 
-def sweep_case(n_users, n_items, n_q, mask_per, seed_tiles, with_flags=False, compact=False):
+def sweep_case(n_users, n_items, n_q, mask_per, seed_tiles, with_flags=False, compact=False, d=64):
     os.environ["CR_TC_SEED_TILES"] = str(seed_tiles)
-    U = torch.randn(n_users, 64, device=dev, generator=g) * 0.125
-    I = torch.randn(n_items, 64, device=dev, generator=g) * 0.125
+    U = torch.randn(n_users, d, device=dev, generator=g) * 0.125
+    I = torch.randn(n_items, d, device=dev, generator=g) * 0.125
     uids = torch.randperm(n_users, device=dev, generator=g)[:n_q].to(torch.int32)
     x = torch.sort(torch.randint(0, n_items - mask_per, (n_q, mask_per), device=dev, generator=g), dim=1).values
     col = (x + torch.arange(mask_per, device=dev)).to(torch.int32).flatten().contiguous()
@@ -51,7 +51,7 @@ def sweep_case(n_users, n_items, n_q, mask_per, seed_tiles, with_flags=False, co
     assert torch.allclose(s, rs, atol=1e-5), "scores differ"
     same = (i.long() == ri).float().mean().item()
     assert same > 0.999, f"ids differ ({same})"
-    print(f"sweep n_q={n_q} n_items={n_items} seed={seed_tiles} flags={with_flags} compact={compact}: ok, refined {int(nref.item())}")
+    print(f"sweep d={d} n_q={n_q} n_items={n_items} seed={seed_tiles} flags={with_flags} compact={compact}: ok, refined {int(nref.item())}")
 
 
 if what in ("sweep", "all"):
@@ -59,6 +59,8 @@ if what in ("sweep", "all"):
     sweep_case(600, 96 * 1100 + 17, 520, 20, 128)            # seed phase on, three units, ragged last tile
     sweep_case(400, 96 * 80, 256, 8, 0, with_flags=True)     # in-kernel flag mask
     sweep_case(400, 96 * 90, 200, 8, 0, compact=True)        # compacted table: per-entry binary search in the bitmap producer
+    sweep_case(500, 64 * 90 + 5, 300, 10, 0, d=128)          # d = 128 instantiation (64-item tiles, four TMA boxes per tile)
+    sweep_case(500, 64 * 1100, 260, 10, 128, with_flags=True, d=128)
     s, i, _ = ops.score_topk(torch.randn(64, 64, device=dev), torch.randn(5000, 64, device=dev), 20, precision=ops.SCORE_EXACT_F32)
     torch.cuda.synchronize()
     print("exact scorer: ok")
@@ -85,6 +87,27 @@ if what in ("spmm", "all"):
         G.spmm(Xd, Y=torch.empty(n, dd, device=dev))
     torch.cuda.synchronize()
     print("spmm (grouped rows + fused long-row chunks + reduce; d=64/32/128/48): ok")
+    # the multi-GPU epilogue on one GPU: this GPU is its own (only) peer — shared-memory staging + TMA bulk stores, both geometries
+    from coldrec_b200 import ops
+    for force_big in (False, True):
+        if force_big:
+            os.environ["CR_SPMM_FORCE_BIG"] = "1"
+        table = torch.full((n + 16, d), float("nan"), device=dev)
+        ptrs = torch.tensor([table.data_ptr()], dtype=torch.int64, device=dev)
+        need = (torch.rand(n, device=dev, generator=g) < 0.7).to(torch.uint8)
+        acc = torch.zeros(n, d, device=dev)
+        ops.spmm_bcast(rowptr, col, val, X, ptrs.data_ptr(), 1, 8, acc=acc, acc_beta=0.0, plan=G.plan(d), bcast_acc=True,
+                       peer_row_split=5000, peer_row_offset_hi=16, peer_need=need)
+        torch.cuda.synchronize()
+        os.environ.pop("CR_SPMM_FORCE_BIG", None)
+        got_lo, got_hi = table[8:8 + 5000], table[16 + 5000:16 + n]
+        sent = need.bool()
+        long_rows = deg > (512 if force_big else 64)
+        assert (acc - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+        both = torch.cat([got_lo, got_hi])
+        assert torch.equal(both[sent], acc[sent]), "staged rows differ from the local result"
+        assert torch.isnan(both[~sent]).all(), "a row was delivered to a GPU that does not read it"
+    print("spmm staged peer stores (TMA bulk copies, two destination ranges, need mask; small + big geometry): ok")
 
 if what in ("train", "all"):
     import coldrec_b200 as cr
@@ -110,4 +133,7 @@ if what in ("towers", "all"):
     ref = torch.tanh(torch.cat([X2, X], 1) @ W.T + b)
     torch.cuda.synchronize()
     assert (y - ref).abs().max().item() < 1e-4
-    print("towers: ok")
+    y3, sp = ops.linear_act_tc(ops.split_tf32(X2), ops.split_tf32(W), b, X2=ops.split_tf32(X), act="tanh", want_split=True)
+    torch.cuda.synchronize()
+    assert (y3 - ref).abs().max().item() < 1e-5
+    print("towers (SIMT + tcgen05 3xTF32): ok")
