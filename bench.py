@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--graph-edges", type=int, default=GRAPH_EDGES)
     ap.add_argument("--cpu-sample-users", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-d128", action="store_true", help="skip the d = 128 (VBPR / AMR two-product) scoring line (N=1; under \"d128\")")
     ap.add_argument("--no-robustness", action="store_true", help="skip the robustness lines (N=1: warm/cold settings, duplicate rows, "
                                                                  "heavy-tailed / norm-sorted item tables; under \"robustness\")")
     ap.add_argument("--configs", default="C1,C2,C3", help="dataset-shaped side lines under \"extra\" (N=1 only): any of C1,C2,C3")
@@ -280,14 +281,14 @@ def run_b200(args):
 
         # end to end through the host-buffer API: H2D of the step's plan from pinned memory, D2H of top-K + metric sums
         hb = HostBatchEvaluator(scorer, TOPN, n_q, n_q * MASK_PER_USER, n_q * GT_PER_USER, device)
-        pinned = [hb.pin(p) for p in distinct]
+        pinned = [hb.pin({k: v.cpu() for k, v in p.items()}) for p in distinct]     # this rank's user group of every host plan
         host_plans = [pinned[k % n_distinct] for k in range(W, W + Ksteps)]
         hb.run(user_tab, item_shard, ib, host_plans[0])
         barrier(world, device)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for hp in host_plans:
-            res = hb.run(user_tab, item_shard, ib, hp)
+        for k, hp in enumerate(host_plans):      # every step copies its own plan; step k+1's copy overlaps step k's sweep
+            res = hb.run(user_tab, item_shard, ib, hp, host_plans[k + 1] if k + 1 < len(host_plans) else None)
         e1.record()
         barrier(world, device)
         e2e_ms = max_over_ranks(e0.elapsed_time(e1), device, world)
@@ -310,10 +311,15 @@ def run_b200(args):
         if world > 1:
             out["check"].update(check_sharded_ids(args, scorer, user_tab, item_shard, ib, plans[-1], S, device, world))
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_score_baseline(user_tab, item_shard, plans_d[W], args.cpu_sample_users)
+            out["cpu_baseline"] = cpu_score_baseline(user_tab, item_shard, plans_d[W], args.cpu_sample_users, args)
             out["gpu_library_baseline"] = library_score_baseline(user_tab, item_shard, plans_d[W])
         if world == 1 and not args.no_robustness:
             out["robustness"] = run_robustness(args, lib, user_tab, item_shard, distinct_plans, device, pk)
+        if world == 1 and not args.no_d128:
+            del item_shard
+            item_shard = None
+            torch.cuda.empty_cache()
+            out["d128"] = run_d128(args, lib, distinct_plans, device, pk)
         del item_shard, plans, plans_d, host_plans, hb, distinct, distinct_plans, pinned
         torch.cuda.empty_cache()
 
@@ -585,6 +591,51 @@ def run_robustness(args, lib, user_tab, item_tab, plans, device, pk, steps=3, wa
         del saved
     return lines
 
+
+# ------------------------------------------------------------------------------------------- d = 128 line (N = 1)
+def run_d128(args, lib, plans, device, pk, steps=3, warmup=2):
+    """VBPR / AMR score with two inner products, P.Q^T + P2.Q2^T = [P|P2].[Q|Q2]^T (model/VBPR.py:68-75): one sweep at d = 128
+    through the d = 128 instantiation of the tcgen05 kernel (64-item tiles, 2 x 16 MMAs per tile), same users, masks and
+    catalogue size as the headline line."""
+    import ctypes
+    from coldrec_b200 import ops
+    g = torch.Generator(device=device).manual_seed(128)
+    U = torch.randn(args.n_users, 128, device=device, generator=g) * 0.09
+    I = torch.randn(args.n_items, 128, device=device, generator=g) * 0.09
+    n_q = plans[0].n_q
+
+    def step(p):
+        s, i, nref = ops.score_topk(U, I, K, user_ids=p.user_ids, mask_rowptr=p.mask_rowptr, mask_col=p.mask_col, precision=ops.SCORE_TF32_CHECKED)
+        ops.rank_metrics(i, p.gt_rowptr, p.gt_col, TOPN)
+        return nref
+    for k in range(warmup):
+        step(plans[k % len(plans)])
+    torch.cuda.synchronize(device)
+    lib.cr_profile_enable(1)
+    l0 = lib.cr_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nref = torch.zeros(1, dtype=torch.int64, device=device)
+    e0.record()
+    for k in range(steps):
+        nref += step(plans[(warmup + k) % len(plans)]).to(torch.int64)
+    e1.record()
+    torch.cuda.synchronize(device)
+    tot, cnt = ctypes.c_double(), ctypes.c_int()
+    lib.cr_profile_read(0, ctypes.byref(tot), ctypes.byref(cnt)); lib.cr_profile_enable(0)
+    ms, sweep_ms = e0.elapsed_time(e1) / steps, tot.value / max(cnt.value, 1)
+    tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+    tfl = 2.0 * n_q * args.n_items * 128 / (sweep_ms * 1e-3) / 1e12 if sweep_ms > 0 else 0.0
+    del U, I
+    torch.cuda.empty_cache()
+    return {"metric": "full-rank users/sec (top-20 over catalog), d = 128", "value": round(n_q / (ms * 1e-3), 1), "unit": "users/s",
+            "ms_per_step": round(ms, 3), "steps": steps, "warmup": warmup, "gpu_launches": int(lib.cr_launch_count() - l0),
+            "config": {"workload": f"VBPR/AMR-shaped two-product scoring as one d=128 sweep: {args.n_users} users x {args.n_items} items, "
+                                   f"{n_q} users/step, same masks / K as the headline line"},
+            "roofline": {"bound": "tensor", "kernel": "score_sweep_tc_kernel<128>", "achieved": round(tfl, 1), "peak": round(tf32_peak, 1),
+                         "unit": "TFLOP/s", "frac": round(tfl / tf32_peak, 4), "launch_ms": round(sweep_ms, 3), "launches": cnt.value,
+                         "flop_per_launch": 2.0 * n_q * args.n_items * 128},
+            "n_refined_all_steps": int(nref.item()), "queries_all_steps": n_q * steps}
+
 # ------------------------------------------------------------------------------------------- multi-GPU result checks
 def check_sharded_ids(args, scorer, user_tab, item_shard, ib, plan, S, device, world, n_sample=4096):
     """N>1: the merged lists this rank holds for the first `n_sample` users of its slice must equal, bit for bit, ONE
@@ -722,22 +773,24 @@ def library_spmm_baseline(G, E0u, E0i):
 
 
 # ------------------------------------------------------------------------------------------- CPU arms (oracle port)
-def cpu_score_baseline(user_tab, item_tab, plan_d, n_sample):
-    """The reference's CPU path (oracle restatement of _evaluate + ranking_evaluation) on a bounded sample."""
-    from oracle import coldrec_oracle as O
+def cpu_score_baseline(user_tab, item_tab, plan_d, n_sample, args):
+    """The reference's CPU path on a bounded sample: its own MF.batch_predict + _evaluate + ranking_evaluation (baseline/_ref,
+    kind "reference"), or the oracle restatement when the reference tree did not travel (kind "port")."""
+    import copy
     torch.set_num_threads(host_threads())
     U, I = user_tab.cpu(), item_tab.cpu()
-    uids = plan_d["user_ids"][:n_sample].cpu().numpy()
-    rp = plan_d["mask_rowptr"][:n_sample + 1].cpu().numpy()
-    col = plan_d["mask_col"][:int(rp[-1])].cpu().numpy().astype(np.int64)
-    grp = plan_d["gt_rowptr"][:n_sample + 1].cpu().numpy()
-    gcol = plan_d["gt_col"][:int(grp[-1])].cpu().numpy().astype(np.int64)
+    a = copy.copy(args)
+    a.cpu_sample_users, a.n_items, a.n_users = n_sample, I.shape[0], U.shape[0]
+    step, kind, sample = reference_step_factory(a, U, I)
+    rp = plan_d["mask_rowptr"][:n_sample + 1].cpu()
+    grp = plan_d["gt_rowptr"][:n_sample + 1].cpu()
+    p = dict(user_ids=plan_d["user_ids"][:n_sample].cpu(), mask_rowptr=rp, mask_col=plan_d["mask_col"][:int(rp[-1])].cpu(),
+             gt_rowptr=grp, gt_col=plan_d["gt_col"][:int(grp[-1])].cpu())
     t0 = time.perf_counter()
-    s, i = O.evaluate_topk_dense_chunked(U, I, uids, rp, col, None, K, user_batch=min(128, n_sample), item_chunk=1 << 20)
-    O.metrics_from_topk(i, grp, gcol, TOPN)
+    step(p)
     dt = time.perf_counter() - t0
-    return {"value": round(n_sample / dt, 2), "unit": "users/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n_sample} users x {I.shape[0]} items (item-chunked torch CPU matmul + mask + topk + metrics), {dt:.1f} s"}
+    return {"value": round(n_sample / dt, 2), "unit": "users/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{sample}, {dt:.1f} s"}
 
 
 def cpu_spmm_baseline(G, E0u, E0i, frac=0.05):

@@ -50,6 +50,7 @@ SIGNATURES = {
     "cr_linear_act_tc_f32": (c_int, [_P, _P, c_int64, c_int, _P, _P, c_int64, c_int, c_int64, _P, _P, c_int64, _P, _P, _P, c_int, c_int, _P,
                                      c_int64, _P, _P, _P, c_int64, _P]),
     "cr_split_tf32": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_int64, _P]),
+    "cr_topk_rows_f32": (c_int, [_P, c_int64, c_int, c_int64, c_int, _P, c_int, _P, _P, _P]),
     "cr_bn_fold_f32": (c_int, [_P, _P, _P, _P, c_float, c_int, _P, _P, _P]),
     "cr_heater_blend_f32": (c_int, [_P, c_int, _P, _P, c_float, c_float, c_int64, c_int, _P, _P]),
     "cr_bpr_workspace_bytes": (c_size_t, [c_int64]),

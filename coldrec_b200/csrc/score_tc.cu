@@ -383,6 +383,14 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
     // maxima, so it is a valid lower bound of the query's KSEL-th best score, and the real sweep — which starts over at
     // tile 0 — begins with a threshold that is already tight.  Virtual tile v = tile v (seed, v < T0) or v - T0 (sweep).
     const int T0 = (p.seed_tiles > 0 && n_local >= 8 * p.seed_tiles) ? p.seed_tiles : 0;
+    // The seed tiles are spread evenly over the unit's item range (every seed_stride-th tile), not its first T0 tiles: on a
+    // table ordered by popularity or norm the head of the range says nothing about the scores to come (r02: a table sorted by
+    // ascending norm ran at 0.66 of the unsorted one with head seeding, the thresholds kept rising to the last tile).
+#ifdef CR_TC_SEED_HEAD                  // (A/B knob: seed from the first T0 tiles, as r01 did)
+    const int seed_stride = 1;
+#else
+    const int seed_stride = T0 > 0 ? n_local / T0 : 1;
+#endif
     const int n_virtual = n_local + T0;
     CR_TL(0);
 
@@ -408,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
                 const int s = i % kStages;
                 if (i >= kStages) mbar_wait(&empty[s], ((i / kStages) - 1) & 1);
                 mbar_expect_tx(&full[s], kTileBytes);
-                const int row = (tile_begin + (i < T0 ? i : i - T0)) * kBN;
+                const int row = (tile_begin + (i < T0 ? i * seed_stride : i - T0)) * kBN;
 #pragma unroll
                 for (int bx = 0; bx < G::kBoxes; ++bx) tma_load_2d(sB + s * kTileBytes + bx * kChunkBytes, &map_i, &full[s], bx * 32, row);
             }
@@ -492,6 +500,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
             for (int j = 0; j < 8; ++j) cur0[j] = (int)(lo8[j] - rlo[j]);
         }
         [[maybe_unused]] long long w_mempty = 0;
+        const bool plain = !p.item_gids && !p.bad_bits;
         uint32_t bits_next = (p.bad_bits && lane < kChunks && n_local > 0) ? __ldg(p.bad_bits + (int64_t)tile_begin * kChunks + lane) : 0u;
         // two passes over the tiles when the seed phase is on: [0, T0) in seed mode, then the whole sweep from tile 0
         for (int pass = (T0 > 0 ? 0 : 1), i = 0; pass < 2; ++pass) {
@@ -515,27 +524,34 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
                     }
                 }
                 uint32_t dirty = 0;
-                const int64_t pos0 = (int64_t)(tile_begin + k) * kBN;
+                const int tstep = pass == 0 ? seed_stride : 1;       // seed pass: every seed_stride-th tile (cursors skip what lies between)
+                const int64_t pos0 = (int64_t)(tile_begin + k * tstep) * kBN;
                 int gid_lo = 0, gid_hi = 0;   // global id range covered by this tile: [gid_lo, gid_hi]
                 // Items nobody may take (flagged by the warm/cold setting, or past the end of the table): one word per
                 // 32-item chunk, the same for every query.  With item flags the words come from the per-call table
                 // (item_bad_bits_kernel) and are fetched ONE TILE AHEAD: r02 measured the former in-loop version — a flag byte
                 // per item loaded, balloted and shuffled by this warp inside every tile — at 0.54 of the unflagged sweep.
-                if (p.bad_bits) {
-                    if (lane < kChunks) sCommon[a * kChunks + lane] = bits_next;
-                    const int kn = (k + 1 < n_pass) ? k + 1 : 0;          // (the sweep pass restarts at tile 0 after the seed pass)
-                    if (lane < kChunks) bits_next = __ldg(p.bad_bits + (int64_t)(tile_begin + kn) * kChunks + lane);
-                } else if (lane < kChunks) {
-                    const int64_t left = p.n_items - (pos0 + lane * 32);
-                    sCommon[a * kChunks + lane] = left >= 32 ? 0u : (left <= 0 ? 0xffffffffu : ~((1u << (int)left) - 1u));
-                }
-                const int n_valid = (int)min((int64_t)kBN, p.n_items - pos0);
-                if (!p.item_gids) {           // contiguous ids
+                if (plain && pos0 + kBN <= p.n_items) {      // common case: contiguous ids, no flags, full tile
                     gid_lo = (int)(p.item_id_base + pos0);
-                    gid_hi = gid_lo + n_valid - 1;
-                } else {                      // compacted table: the ids of its first and last row in this tile
-                    gid_lo = __ldg(p.item_gids + pos0);
-                    gid_hi = __ldg(p.item_gids + pos0 + n_valid - 1);
+                    gid_hi = gid_lo + kBN - 1;
+                    if (lane < kChunks) sCommon[a * kChunks + lane] = 0;
+                } else {
+                    if (p.bad_bits) {
+                        if (lane < kChunks) sCommon[a * kChunks + lane] = bits_next;
+                        const int kn = (k + 1 < n_pass) ? (k + 1) * tstep : 0;   // (the sweep pass restarts at tile 0 after the seed pass)
+                        if (lane < kChunks) bits_next = __ldg(p.bad_bits + (int64_t)(tile_begin + kn) * kChunks + lane);
+                    } else if (lane < kChunks) {
+                        const int64_t left = p.n_items - (pos0 + lane * 32);
+                        sCommon[a * kChunks + lane] = left >= 32 ? 0u : (left <= 0 ? 0xffffffffu : ~((1u << (int)left) - 1u));
+                    }
+                    const int n_valid = (int)min((int64_t)kBN, p.n_items - pos0);
+                    if (!p.item_gids) {           // contiguous ids
+                        gid_lo = (int)(p.item_id_base + pos0);
+                        gid_hi = gid_lo + n_valid - 1;
+                    } else {                      // compacted table: the ids of its first and last row in this tile
+                        gid_lo = __ldg(p.item_gids + pos0);
+                        gid_hi = __ldg(p.item_gids + pos0 + n_valid - 1);
+                    }
                 }
                 __syncwarp();
 #pragma unroll
@@ -609,7 +625,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
             CR_WAIT(w_mfull, &mfull[ms], (i / kMaskStages) & 1);
             tc_fence_after();
             const bool seeding = i < T0;
-            const int64_t pos0 = (int64_t)(tile_begin + (seeding ? i : i - T0)) * kBN;
+            const int64_t pos0 = (int64_t)(tile_begin + (seeding ? i * seed_stride : i - T0)) * kBN;
             const uint32_t acc_addr = tmem_base + lane_addr + kTmemAcc + a * (2 * kBN) + t * kBN;
             uint32_t rbuf[2][32];
             if constexpr (DBG) {

@@ -555,7 +555,13 @@ int launch_spmm(const SpmmArgs& a) {
             // rows per warp so that the grid still covers the SMs (CiteULike-shaped, 22.5k rows: 22 -> 88 CTAs)
             const bool big = a.n_rows >= (int64_t)148 * 24 * 128 || getenv("CR_SPMM_FORCE_BIG");   // (test knob: wide geometry on small graphs)
             const int rows_per_warp = big ? 128 : 32;
-            const int32_t* warp_rows = (big && !getenv("CR_SPMM_FIXED_ROWS")) ? a.warp_rows : nullptr;     // (A/B knob)
+            // Work-balanced ranges pay where a fixed 128 rows per warp leaves few, uneven warps — the row block of a 4- or 8-way
+            // partition (r02, 8 GPUs: 11.3 -> 8.8 ms per propagation).  On the whole 11M-row graph (86k warps, 18 waves) the fixed
+            // mapping is ~1 % faster (29.9 vs 30.2 ms, one box), so it stays there: balanced below 8 waves of fixed warps.
+            const bool few_warps = a.n_rows < (int64_t)148 * 4 * 8 * 8 * 128;
+            const char* force = getenv("CR_SPMM_FIXED_ROWS");          // (A/B knob: 1 = always fixed, 0 = always balanced)
+            const bool balanced = big && (force ? force[0] == '0' : few_warps);
+            const int32_t* warp_rows = balanced ? a.warp_rows : nullptr;
             const int64_t n_bal = balanced_warps(a.n_rows, a.nnz);
             const int64_t warps = warp_rows ? n_bal : (a.n_rows + rows_per_warp - 1) / rows_per_warp;
             // long-row chunks ride in the first CTAs of the same launch (the plan lives on the device: size by its upper bound)

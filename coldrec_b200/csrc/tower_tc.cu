@@ -12,13 +12,20 @@
 // The split of a constant table (item content: 20,519 x 2,738 at XING shape) is done once (cr_split_tf32) and reused;
 // a layer's epilogue can emit its output already split, so a tower chain never runs a separate split pass in between.
 //
-// One CTA = 128 rows x all n_out (<= 256) outputs; K is walked in 32-float chunks (one SWIZZLE_128B TMA box per operand
-// and half: A.hi, A.lo 16 KB each, W.hi, W.lo n_pad x 128 B each) through a ring of shared-memory stages.  The two-segment
+// Accumulation.  The tensor core adds each MMA's result to the TMEM accumulator with truncation, not round-to-nearest: over the
+// 1056 MMAs of a K = 2,802 layer that bias reached 1.7e-5 (r02, first version: one accumulator for the whole K loop) — more
+// than the whole parity budget.  So the K loop is cut into blocks of kBlockChunks chunks (24 MMAs): each block accumulates
+// from zero into one of two TMEM accumulator stages, and the epilogue warps drain a finished block into fp32 running sums
+// held in REGISTERS (round-to-nearest adds) while the next block is being issued.  Error now: a few 1e-7.
+//
+// One CTA = 128 rows x NB (64 or 128) outputs (grid.y walks wider layers); K is walked in 32-float chunks (one SWIZZLE_128B
+// TMA box per operand and half: A.hi, A.lo 16 KB each, W.hi, W.lo NB x 128 B each) through a ring of shared-memory stages.  The two-segment
 // K loop is the torch.cat of DropoutNet.py:199-202 ([V | content]): chunks of X1 first, then chunks of X2 against the W
 // columns starting at d1; TMA zero-fills past the end of a segment / of W's rows, so no width needs padding to 32.
 //   warp 0      TMA producer
-//   warp 1      TMEM allocation + MMA issuer (one elected lane): 4 slices x 3 MMAs (M128 N=n_pad K8, kind::tf32) per chunk
-//   warps 2-5   epilogue: thread = one row = one TMEM lane; tcgen05.ld 32 columns at a time, bias / folded BN / activation,
+//   warp 1      TMEM allocation + MMA issuer (one elected lane): 4 slices x 3 MMAs (M128 N=NB K8, kind::tf32) per chunk
+//   warps 2-5   epilogue: thread = one row = one TMEM lane; per K block tcgen05.ld 32 columns at a time into the running sums;
+//               after the last block bias / folded BN / activation,
 //               row-major stores of Y and (optionally) of its hi / lo split; the row map yrow is the item_emb[cold_idx]
 //               scatter of GAR.py:44-46.
 #include <cuda.h>
@@ -35,7 +42,7 @@ constexpr int kABytes = kBM * 128;          // one A box: 128 rows x 32 fp32
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 200 * 1024;
 constexpr uint32_t kSpinLimit = 1u << 26;
-constexpr int kTmemCols = 256;
+constexpr int kBlockChunks = 2;             // K chunks (x 12 MMAs) accumulated in TMEM before the block is drained into registers
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -43,6 +50,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -116,7 +126,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 struct TowerTcParams {
     int64_t n_rows;
-    int n_out, n_pad;              // outputs; padded to a multiple of 16 (the MMA N)
+    int n_out;                     // outputs of the layer (grid.y x NB covers them)
     int chunks1, chunks2, d1;      // 32-float K chunks of the two segments; W column where segment 2 starts
     const float* bias; const float* scale; const float* shift; int act;
     float* Y; int64_t ldy; const int32_t* yrow;
@@ -124,26 +134,31 @@ struct TowerTcParams {
     uint32_t idesc; int stages;
 };
 
+template <int NB>
 __global__ void __launch_bounds__(kThreads, 1)
 tower_layer_tc_kernel(const __grid_constant__ CUtensorMap mapA1h, const __grid_constant__ CUtensorMap mapA1l,
                       const __grid_constant__ CUtensorMap mapA2h, const __grid_constant__ CUtensorMap mapA2l,
                       const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl, const TowerTcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const int b_bytes = p.n_pad * 128;
-    const int stage_bytes = 2 * kABytes + 2 * b_bytes;
+    constexpr int b_bytes = NB * 128;
+    constexpr int stage_bytes = 2 * kABytes + 2 * b_bytes;
+    constexpr int kTmemCols = 2 * NB;          // two accumulator stages
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* full = bars;                     // [stages] TMA -> MMA
     uint64_t* empty = bars + kMaxStages;       // [stages] MMA -> TMA
-    uint64_t* acc_full = bars + 2 * kMaxStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
+    uint64_t* tfull = bars + 2 * kMaxStages;   // [2] MMA -> epilogue: a K block is complete in accumulator stage a
+    uint64_t* tempty = tfull + 2;              // [2] epilogue -> MMA: stage a has been drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     const int warp = __shfl_sync(CR_FULL_MASK, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     const int64_t m0 = (int64_t)blockIdx.x * kBM;
+    const int n0 = blockIdx.y * NB;            // first output column of this CTA
     const int n_chunks = p.chunks1 + p.chunks2;
+    const int n_blocks = (n_chunks + kBlockChunks - 1) / kBlockChunks;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(acc_full, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -168,91 +183,111 @@ tower_layer_tc_kernel(const __grid_constant__ CUtensorMap mapA1h, const __grid_c
                 tma_load_2d(st, seg2 ? &mapA2h : &mapA1h, &full[s], kk, (int)m0);
                 tma_load_2d(st + kABytes, seg2 ? &mapA2l : &mapA1l, &full[s], kk, (int)m0);
                 const int wcol = seg2 ? p.d1 + kk : kk;
-                tma_load_2d(st + 2 * kABytes, &mapWh, &full[s], wcol, 0);
-                tma_load_2d(st + 2 * kABytes + b_bytes, &mapWl, &full[s], wcol, 0);
+                tma_load_2d(st + 2 * kABytes, &mapWh, &full[s], wcol, n0);
+                tma_load_2d(st + 2 * kABytes + b_bytes, &mapWl, &full[s], wcol, n0);
             }
         }
     } else if (warp == 1) {
         const bool leader = elect_one();
         for (int c = 0; c < n_chunks; ++c) {
-            const int s = c % p.stages;
+            const int s = c % p.stages, blk = c / kBlockChunks, a = blk & 1;
+            const bool first = c % kBlockChunks == 0, last = (c % kBlockChunks == kBlockChunks - 1) || c == n_chunks - 1;
+            if (first && blk >= 2) mbar_wait(&tempty[a], ((blk >> 1) - 1) & 1);
             mbar_wait(&full[s], (c / p.stages) & 1);
             tc_fence_after();
             if (leader) {
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + kABytes);
                 const uint64_t b_hi = smem_desc_sw128(sa + 2 * kABytes), b_lo = smem_desc_sw128(sa + 2 * kABytes + b_bytes);
+                const uint32_t d = tmem_base + a * NB;
 #pragma unroll
                 for (int k = 0; k < kBK / 8; ++k) {          // a K = 8 slice is 32 bytes further along the swizzled row: +2 in 16-byte units
-                    umma_tf32_ss(tmem_base, a_hi + 2 * k, b_hi + 2 * k, p.idesc, (c > 0 || k > 0) ? 1u : 0u);
-                    umma_tf32_ss(tmem_base, a_lo + 2 * k, b_hi + 2 * k, p.idesc, 1u);
-                    umma_tf32_ss(tmem_base, a_hi + 2 * k, b_lo + 2 * k, p.idesc, 1u);
+                    umma_tf32_ss(d, a_hi + 2 * k, b_hi + 2 * k, p.idesc, (!first || k > 0) ? 1u : 0u);
+                    umma_tf32_ss(d, a_lo + 2 * k, b_hi + 2 * k, p.idesc, 1u);
+                    umma_tf32_ss(d, a_hi + 2 * k, b_lo + 2 * k, p.idesc, 1u);
                 }
                 umma_commit(&empty[s]);
-                if (c == n_chunks - 1) umma_commit(acc_full);
+                if (last) umma_commit(&tfull[a]);
             }
             __syncwarp();
         }
     } else {
-        // ===== epilogue: thread = one row = one TMEM lane =====
+        // ===== epilogue: thread = one row = one TMEM lane; running sums of the K blocks in registers =====
         const int quad = warp & 3;
         const int64_t row = m0 + quad * 32 + lane;
         const bool valid = row < p.n_rows;
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        const int64_t orow = valid ? (p.yrow ? (int64_t)__ldg(p.yrow + row) : row) : 0;
-        float* yp = p.Y ? p.Y + orow * p.ldy : nullptr;
-        float* hp = p.Yhi ? p.Yhi + row * p.ldh : nullptr;
-        float* lp = p.Ylo ? p.Ylo + row * p.ldh : nullptr;
-        const bool vec = (p.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.Y) & 15u) == 0);
-        const bool vech = (p.ldh % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.Yhi) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(p.Ylo) & 15u) == 0);
-        for (int c0 = 0; c0 < p.n_pad; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + c0, r);
-            if (!valid) continue;
+        float run[NB];
 #pragma unroll
-            for (int x = 0; x < 32; x += 4) {
-                float v[4], h[4], l[4];
+        for (int x = 0; x < NB; ++x) run[x] = 0.f;
+        for (int blk = 0; blk < n_blocks; ++blk) {
+            const int a = blk & 1;
+            mbar_wait(&tfull[a], (blk >> 1) & 1);
+            tc_fence_after();
 #pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                    const int o = c0 + x + y;
-                    float t = 0.f;
-                    if (o < p.n_out) {
-                        t = __uint_as_float(r[x + y]) + (p.bias ? __ldg(p.bias + o) : 0.f);
-                        if (p.scale) t = t * __ldg(p.scale + o) + __ldg(p.shift + o);
-                        t = apply_act(t, p.act);
-                    }
-                    v[y] = t;
-                    h[y] = tf32_rna(t);
-                    l[y] = t - h[y];
-                }
-                const int o0 = c0 + x;
-                if (o0 >= p.n_out) break;
-                if (o0 + 4 <= p.n_out) {
-                    if (yp) {
-                        if (vec) *reinterpret_cast<float4*>(yp + o0) = make_float4(v[0], v[1], v[2], v[3]);
-                        else { yp[o0] = v[0]; yp[o0 + 1] = v[1]; yp[o0 + 2] = v[2]; yp[o0 + 3] = v[3]; }
-                    }
-                    if (hp) {
-                        if (vech) {
-                            *reinterpret_cast<float4*>(hp + o0) = make_float4(h[0], h[1], h[2], h[3]);
-                            *reinterpret_cast<float4*>(lp + o0) = make_float4(l[0], l[1], l[2], l[3]);
-                        } else {
+            for (int c0 = 0; c0 < NB; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + a * NB + c0, r);
 #pragma unroll
-                            for (int y = 0; y < 4; ++y) { hp[o0 + y] = h[y]; lp[o0 + y] = l[y]; }
+                for (int x = 0; x < 32; ++x) run[c0 + x] += __uint_as_float(r[x]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[a]);
+        }
+        if (valid) {
+            const int64_t orow = p.yrow ? (int64_t)__ldg(p.yrow + row) : row;
+            float* yp = p.Y ? p.Y + orow * p.ldy : nullptr;
+            float* hp = p.Yhi ? p.Yhi + row * p.ldh : nullptr;
+            float* lp = p.Ylo ? p.Ylo + row * p.ldh : nullptr;
+            const bool vec = (p.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.Y) & 15u) == 0);
+            const bool vech = (p.ldh % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.Yhi) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(p.Ylo) & 15u) == 0);
+#pragma unroll
+            for (int x = 0; x < NB; x += 4) {
+                const int o0 = n0 + x;
+                if (o0 < p.n_out) {
+                    float v[4], h[4], l[4];
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        const int o = o0 + y;
+                        float t = 0.f;
+                        if (o < p.n_out) {
+                            t = run[x + y] + (p.bias ? __ldg(p.bias + o) : 0.f);
+                            if (p.scale) t = t * __ldg(p.scale + o) + __ldg(p.shift + o);
+                            t = apply_act(t, p.act);
                         }
+                        v[y] = t;
+                        h[y] = tf32_rna(t);
+                        l[y] = t - h[y];
                     }
-                } else {
-                    for (int y = 0; o0 + y < p.n_out; ++y) {
-                        if (yp) yp[o0 + y] = v[y];
-                        if (hp) { hp[o0 + y] = h[y]; lp[o0 + y] = l[y]; }
+                    if (o0 + 4 <= p.n_out) {
+                        if (yp) {
+                            if (vec) *reinterpret_cast<float4*>(yp + o0) = make_float4(v[0], v[1], v[2], v[3]);
+                            else { yp[o0] = v[0]; yp[o0 + 1] = v[1]; yp[o0 + 2] = v[2]; yp[o0 + 3] = v[3]; }
+                        }
+                        if (hp) {
+                            if (vech) {
+                                *reinterpret_cast<float4*>(hp + o0) = make_float4(h[0], h[1], h[2], h[3]);
+                                *reinterpret_cast<float4*>(lp + o0) = make_float4(l[0], l[1], l[2], l[3]);
+                            } else {
+#pragma unroll
+                                for (int y = 0; y < 4; ++y) { hp[o0 + y] = h[y]; lp[o0 + y] = l[y]; }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) {
+                            if (o0 + y < p.n_out) {
+                                if (yp) yp[o0 + y] = v[y];
+                                if (hp) { hp[o0 + y] = h[y]; lp[o0 + y] = l[y]; }
+                            }
+                        }
                     }
                 }
             }
-        }
-        // the split tables are padded to ldh columns: the padding must read as zero in the next layer's K loop
-        if (valid && hp) {
-            for (int o = p.n_out; o < p.ldh; ++o) { hp[o] = 0.f; lp[o] = 0.f; }
+            // the split tables are padded to ldh columns: the padding must read as zero in the next layer's K loop
+            if (hp && n0 + NB >= p.n_out) {
+                for (int o = p.n_out; o < p.ldh; ++o) { hp[o] = 0.f; lp[o] = 0.f; }
+            }
         }
     }
     tc_fence_before();
@@ -337,7 +372,7 @@ int cr_linear_act_tc_f32(const float* X1hi, const float* X1lo, int64_t ld1, int 
     if (!X1hi || !X1lo || !Whi || !Wlo || n_rows < 0 || d1 <= 0 || d2 < 0 || (d2 > 0 && (!X2hi || !X2lo)) || n_out <= 0) return CR_ERR_ARG;
     if ((!Y && !Yhi) || ((Yhi == nullptr) != (Ylo == nullptr)) || (Y && ldy < n_out) || (Yhi && ldh < n_out)) return CR_ERR_ARG;
     if (((scale == nullptr) != (shift == nullptr)) || ldw < d1 + d2 || ld1 < d1 || (d2 > 0 && ld2 < d2)) return CR_ERR_ARG;
-    if (act < CR_ACT_NONE || act > CR_ACT_LEAKY_RELU || n_out > 256 || n_rows > 0x7fffffffLL) return CR_ERR_UNSUPPORTED;
+    if (act < CR_ACT_NONE || act > CR_ACT_LEAKY_RELU || n_out > 65535 * 64 || n_rows > 0x7fffffffLL) return CR_ERR_UNSUPPORTED;
     if (yrow && Yhi) return CR_ERR_UNSUPPORTED;       // split outputs are written in input row order
     if (!tma_ok(X1hi, ld1) || !tma_ok(X1lo, ld1) || !tma_ok(Whi, ldw) || !tma_ok(Wlo, ldw)) return CR_ERR_ALIGN;
     if (d2 > 0 && (!tma_ok(X2hi, ld2) || !tma_ok(X2lo, ld2))) return CR_ERR_ALIGN;
@@ -345,15 +380,15 @@ int cr_linear_act_tc_f32(const float* X1hi, const float* X1lo, int64_t ld1, int 
     if (rc != CR_OK) return rc;
     if (n_rows == 0) return CR_OK;
     TowerTcParams p{};
-    p.n_rows = n_rows; p.n_out = n_out; p.n_pad = (n_out + 15) / 16 * 16;
+    p.n_rows = n_rows; p.n_out = n_out;
     p.chunks1 = (d1 + kBK - 1) / kBK; p.chunks2 = (d2 + kBK - 1) / kBK; p.d1 = d1;
     p.bias = bias; p.scale = scale; p.shift = shift; p.act = act;
     p.Y = Y; p.ldy = ldy; p.yrow = yrow; p.Yhi = Yhi; p.Ylo = Ylo; p.ldh = ldh;
-    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-    const int stage_bytes = 2 * kABytes + 2 * p.n_pad * 128;
+    const int NB = n_out <= 64 ? 64 : 128;
+    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    const int stage_bytes = 2 * kABytes + 2 * NB * 128;
     p.stages = (kSmemBudget - 1024) / stage_bytes;
     if (p.stages > kMaxStages) p.stages = kMaxStages;
-    if (p.stages < 2) return CR_ERR_UNSUPPORTED;
     const int smem = p.stages * stage_bytes + 1024;
     CUtensorMap a1h, a1l, a2h, a2l, wh, wl;
     if ((rc = make_map(&a1h, X1hi, n_rows, d1, ld1, kBM)) != CR_OK) return rc;
@@ -364,11 +399,16 @@ int cr_linear_act_tc_f32(const float* X1hi, const float* X1lo, int64_t ld1, int 
     } else {
         a2h = a1h; a2l = a1l;
     }
-    if ((rc = make_map(&wh, Whi, n_out, d1 + d2, ldw, p.n_pad)) != CR_OK) return rc;
-    if ((rc = make_map(&wl, Wlo, n_out, d1 + d2, ldw, p.n_pad)) != CR_OK) return rc;
-    CR_CUDA_TRY(cudaFuncSetAttribute(tower_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    const unsigned grid = (unsigned)((n_rows + kBM - 1) / kBM);
-    tower_layer_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(a1h, a1l, a2h, a2l, wh, wl, p);
+    if ((rc = make_map(&wh, Whi, n_out, d1 + d2, ldw, NB)) != CR_OK) return rc;
+    if ((rc = make_map(&wl, Wlo, n_out, d1 + d2, ldw, NB)) != CR_OK) return rc;
+    const dim3 grid((unsigned)((n_rows + kBM - 1) / kBM), (unsigned)((n_out + NB - 1) / NB));
+    if (NB == 64) {
+        CR_CUDA_TRY(cudaFuncSetAttribute(tower_layer_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        tower_layer_tc_kernel<64><<<grid, kThreads, smem, (cudaStream_t)stream>>>(a1h, a1l, a2h, a2l, wh, wl, p);
+    } else {
+        CR_CUDA_TRY(cudaFuncSetAttribute(tower_layer_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        tower_layer_tc_kernel<128><<<grid, kThreads, smem, (cudaStream_t)stream>>>(a1h, a1l, a2h, a2l, wh, wl, p);
+    }
     CR_LAUNCH_CHECK("tower_layer_tc_kernel");
     return CR_OK;
 }

@@ -87,16 +87,21 @@ class ShardedFullRankScorer:
         lo, hi = self.user_slice(plan.n_q)
         return self._merge(gs[:, lo:hi].contiguous(), gi[:, lo:hi].contiguous())
 
-    def metrics(self, ids_slice: torch.Tensor, plan: EvalPlan, Ns: Sequence[int], rounded: bool = True):
-        """Hit/Precision/Recall/NDCG over all eval users from per-rank partial sums (one all-reduce)."""
-        lo, hi = self.user_slice(plan.n_q) if self.world > 1 else (0, plan.n_q)
+    def metrics(self, ids_slice: torch.Tensor, plan: EvalPlan, Ns: Sequence[int], rounded: bool = True, n_q_total: Optional[int] = None):
+        """Hit/Precision/Recall/NDCG over all eval users from per-rank partial sums (one all-reduce).  With ``n_q_total`` the
+        plan holds only this rank's user group (see ``GridShardedFullRankScorer.topk``)."""
+        n_q = plan.n_q if n_q_total is None else n_q_total
+        lo, hi = self.user_slice(n_q) if self.world > 1 else (0, n_q)
+        if n_q_total is not None and self.world > 1:          # positions inside the group plan
+            g_lo = self.group_slice(n_q)[0] if hasattr(self, "group_slice") else 0
+            lo, hi = lo - g_lo, hi - g_lo
         base = plan.gt_rowptr[lo]
         rp = (plan.gt_rowptr[lo:hi + 1] - base).contiguous()
         col = plan.gt_col[int(base):int(plan.gt_rowptr[hi])].contiguous()
         sums = self._metrics(ids_slice, rp, col, list(Ns))
         if self.world > 1:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
-        return metrics_from_sums(sums.cpu().numpy(), plan.n_q, Ns, rounded)
+        return metrics_from_sums(sums.cpu().numpy(), n_q, Ns, rounded)
 
 
 class UserShardedFullRankScorer(ShardedFullRankScorer):
@@ -174,11 +179,14 @@ class GridShardedFullRankScorer(ShardedFullRankScorer):
         lo, hi = shard_range(g_hi - g_lo, self.ishard, self.S)
         return g_lo + lo, g_lo + hi
 
-    def topk(self, user_tab, item_shard: torch.Tensor, item_begin: int, plan: EvalPlan, item_flags=None):
+    def topk(self, user_tab, item_shard: torch.Tensor, item_begin: int, plan: EvalPlan, item_flags=None, n_q_total: Optional[int] = None):
         """item_shard = rows ``item_range(n_items)`` of the item table (``item_begin`` = its first id); plan covers ALL
-        eval users.  Returns (scores, ids) [n_slice, K] for users ``user_slice(plan.n_q)``."""
-        g_lo, g_hi = self.group_slice(plan.n_q)
-        sub_plan = plan if self.n_groups == 1 else plan.slice(g_lo, g_hi)
+        eval users — or, with ``n_q_total`` given, only this rank's user group ``group_slice(n_q_total)`` (what a host batch
+        pipeline copies to this GPU).  Returns (scores, ids) [n_slice, K] for users ``user_slice(n_q)``."""
+        g_lo, g_hi = self.group_slice(plan.n_q if n_q_total is None else n_q_total)
+        if n_q_total is not None and plan.n_q != g_hi - g_lo:
+            raise ValueError(f"group plan has {plan.n_q} users, this rank's group has {g_hi - g_lo}")
+        sub_plan = plan if (self.n_groups == 1 or n_q_total is not None) else plan.slice(g_lo, g_hi)
         s, i = self._local_topk(user_tab, item_shard, item_begin, sub_plan, item_flags)
         if self.S == 1:
             return s, i

@@ -9,6 +9,7 @@ in its epilogue.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -35,12 +36,35 @@ def knn_inner_product(query, value, k: int, device="cuda:0", exclude_self: bool 
         raise ValueError(f"query width {q.shape[1]} != value width {v.shape[1]}")
     if k > v.shape[0] - (1 if exclude_self else 0):
         raise ValueError(f"k={k} exceeds the number of candidates")
+    if q.shape[1] > 128 and not os.environ.get("CR_KNN_SIMT"):
+        return _knn_wide(q, v, k, exclude_self)
     rowptr = col = None
     if exclude_self:
         rowptr = torch.arange(q.shape[0] + 1, dtype=torch.int64, device=q.device)
         col = torch.arange(q.shape[0], dtype=torch.int32, device=q.device)
-    s, i, _ = ops.score_topk(q, v, k, mask_rowptr=rowptr, mask_col=col, precision=ops.SCORE_EXACT_F32)
+    # d = 64 / 128: the tcgen05 sweep (TF32-checked: exact fp32 scores of a proven top-k); other widths <= 128: exact fp32 kernel
+    s, i, _ = ops.score_topk(q, v, k, mask_rowptr=rowptr, mask_col=col,
+                             precision=ops.SCORE_TF32_CHECKED if q.shape[1] in (64, 128) else ops.SCORE_EXACT_F32)
     return s, i
+
+
+def _knn_wide(q: torch.Tensor, v: torch.Tensor, k: int, exclude_self: bool, block_bytes: int = 512 << 20):
+    """Content tables wider than the fused sweep's TMEM-resident query tiles (CiteULike 300, XING 2,738): inner products of a
+    block of queries against every value on the tensor cores at fp32 accuracy (``cr_linear_act_tc_f32``, the value table as
+    the weight matrix — 3xTF32 with K-block drains), then the row-wise top-k kernel; the (queries x values) block is the only
+    score storage and is reused from block to block."""
+    vs = ops.split_tf32(v)
+    n_q, n_v = q.shape[0], v.shape[0]
+    rows = max(128, min(n_q, block_bytes // (4 * max(n_v, 1)) // 128 * 128))
+    S = torch.empty((min(rows, n_q), n_v), dtype=torch.float32, device=q.device)
+    out_s = torch.empty((n_q, k), dtype=torch.float32, device=q.device)
+    out_i = torch.empty((n_q, k), dtype=torch.int32, device=q.device)
+    for lo in range(0, n_q, rows):
+        hi = min(n_q, lo + rows)
+        ops.linear_act_tc(ops.split_tf32(q[lo:hi]), vs, None, out=S[:hi - lo])
+        ex = torch.arange(lo, hi, dtype=torch.int32, device=q.device) if exclude_self else None
+        out_s[lo:hi], out_i[lo:hi] = ops.topk_rows(S[:hi - lo], k, exclude_col=ex)
+    return out_s, out_i
 
 
 def precompute_knn_neighbors(data, cold_object: str, knn_num: int, device="cuda:0") -> np.ndarray:

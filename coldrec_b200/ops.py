@@ -14,7 +14,7 @@ import torch
 from . import _lib
 
 __all__ = ["spmm_plan", "spmm", "spmm_bcast", "score_topk", "topk_merge", "fill_masked", "gather_rows", "rank_metrics", "linear_act", "bn_fold",
-           "SplitTable", "split_tf32", "linear_act_tc",
+           "SplitTable", "split_tf32", "linear_act_tc", "topk_rows",
            "heater_blend", "bpr_fwd_bwd", "adam_step", "sample_pairwise", "SCORE_EXACT_F32", "SCORE_TF32_CHECKED"]
 
 SCORE_EXACT_F32 = _lib.SCORE_EXACT_F32
@@ -401,6 +401,25 @@ def linear_act_tc(X1: SplitTable, W: SplitTable, bias=None, *, X2: Optional[Spli
                                       _ptr(None if sp is None else sp.lo), 0 if sp is None else sp.hi.stride(0), _stream(dev))
     _lib.check(rc, "cr_linear_act_tc_f32")
     return out, sp
+
+
+def topk_rows(S: torch.Tensor, K: int, exclude_col=None, col_id_base: int = 0):
+    """Row-wise top-K of a dense score block: (scores [n_rows, K], ids [n_rows, K] int32), (score desc, id asc)."""
+    lib = _lib.load()
+    S = _req(S, torch.float32, "S", contiguous=False)
+    if S.dim() != 2 or S.stride(1) != 1:
+        raise ValueError("S must be 2-D with unit inner stride")
+    exclude_col = _req(exclude_col, torch.int32, "exclude_col", optional=True)
+    dev = _same_device(S, exclude_col)
+    n_rows, n_cols = S.shape
+    out_s = torch.empty((n_rows, K), dtype=torch.float32, device=dev)
+    out_i = torch.empty((n_rows, K), dtype=torch.int32, device=dev)
+    if n_rows:
+        with torch.cuda.device(dev):
+            rc = lib.cr_topk_rows_f32(_ptr(S), n_rows, n_cols, max(S.stride(0), n_cols), K, _ptr(exclude_col), int(col_id_base), _ptr(out_s),
+                                      _ptr(out_i), _stream(dev))
+        _lib.check(rc, "cr_topk_rows_f32")
+    return out_s, out_i
 
 
 def bn_fold(gamma, beta, mean, var, eps: float):

@@ -202,6 +202,12 @@ CR_API int cr_linear_act_tc_f32(const float *X1hi, const float *X1lo, int64_t ld
  * ld_dst >= cols, columns [cols, ld_dst) zeroed (pads a 2,738-wide content table to a TMA-legal stride). */
 CR_API int cr_split_tf32(const float *src, int64_t ld_src, int64_t rows, int cols, float *hi, float *lo, int64_t ld_dst,
                   void *stream);
+/* Row-wise top-K of a dense score block S [n_rows, n_cols] (row stride ld): out ids = col_id_base + column, ordered by
+ * (score desc, id asc); exclude_col (nullable, one column per row) is skipped — the "not myself" of a kNN graph.  With
+ * cr_linear_act_tc_f32 producing S = Q . V^T this is the brute-force inner-product search of model/KNN.py:63-77
+ * (faiss.IndexFlatIP) and model/FSGNN.py:106-152 for content tables too wide for the fused sweep (d = 300 / 2,738). */
+CR_API int cr_topk_rows_f32(const float *S, int64_t n_rows, int n_cols, int64_t ld, int K, const int32_t *exclude_col,
+                     int col_id_base, float *out_score, int32_t *out_id, void *stream);
 /* scale = gamma / sqrt(var + eps); shift = beta - mean * scale   (eval BatchNorm1d, DropoutNet.py:226-230) */
 CR_API int cr_bn_fold_f32(const float *gamma, const float *beta, const float *mean, const float *var, float eps, int n,
                    float *scale, float *shift, void *stream);

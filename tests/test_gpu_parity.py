@@ -446,7 +446,7 @@ def test_tower_layer_tc_3xtf32_matches_fp64(shape):
     ref = np.tanh(pre)
     y, sp = ops.linear_act_tc(ops.split_tf32(cu(X1)), ops.split_tf32(cu(W)), cu(b), X2=ops.split_tf32(cu(X2)) if d2 else None,
                               scale=cu(sc), shift=cu(sh), act="tanh", want_split=True)
-    assert_normwise(y, ref.astype(np.float32), tol=2e-6)
+    assert_normwise(y, ref.astype(np.float32), tol=5e-6)          # half of the 1e-5 parity budget (K = 2,738 dense rows: ~3e-6)
     # the split output is the same value, exactly: hi + lo == y, hi is TF32-representable, padding columns are zero
     hi, lo = sp.hi.cpu().numpy(), sp.lo.cpu().numpy()
     assert np.array_equal((hi.astype(np.float64) + lo)[:, :n_out].astype(np.float32), y.cpu().numpy())

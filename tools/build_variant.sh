@@ -10,7 +10,7 @@ make -s -j8 >/dev/null
 nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fvisibility=hidden -Xptxas -v --expt-relaxed-constexpr \
     "$@" -c "$src" -o "variants/${name}_${src%.cu}.o" 2> "variants/${name}.ptxas.log"
 objs=""
-for o in abi spmm score_simt score_tc score_api metrics towers tower_tc train; do
+for o in abi spmm score_simt score_tc score_api metrics towers tower_tc rowtopk train; do
     if [ "$o.cu" == "$src" ]; then objs="$objs variants/${name}_$o.o"; else objs="$objs $o.o"; fi
 done
 nvcc -shared -gencode arch=compute_100a,code=sm_100a -cudart static -o "variants/lib_${name}.so" $objs
