@@ -573,6 +573,22 @@ def run_robustness(args, lib, user_tab, item_tab, plans, device, pk, steps=3, wa
     timed("warm setting, cold items compacted away before the sweep (item_gids)", compacted(FLAG_COLD), n_warm)
     timed("cold setting, 80% warm items masked inside the kernel", kernel_flags(FLAG_WARM), n_items)
     timed("cold setting, warm items compacted away before the sweep (item_gids)", compacted(FLAG_WARM), n_cold)
+    # the exact fp32 FFMA kernel (CR_SCORE_EXACT_F32: the product path for d not in {64, 128}, K > 52, and every query whose
+    # margin proof fails): 4,096 of the step's queries against the whole catalogue; bound = fp32 FMA rate of the CUDA cores
+    # (148 SMs x 128 lanes x 2 x SM clock: ~72 TFLOP/s at 1.9 GHz), not the tensor pipe
+    try:
+        nx = min(4096, n_q)
+        px = plans[0]
+        sub = px.slice(0, nx)
+        fx = lambda: ops.score_topk(user_tab, item_tab, K, user_ids=sub.user_ids, mask_rowptr=sub.mask_rowptr, mask_col=sub.mask_col,
+                                    precision=ops.SCORE_EXACT_F32)
+        ex_ms = _event_ms(fx, iters=2, warm=1)
+        ex_tfl = 2.0 * nx * n_items * D / (ex_ms * 1e-3) / 1e12
+        lines.append({"case": f"exact fp32 FFMA kernel (score_topk_exact_kernel), {nx} queries x {n_items} items", "users_per_s": round(nx / (ex_ms * 1e-3), 1),
+                      "ms_per_step": round(ex_ms, 3), "items_swept": n_items, "sweep_tflops": round(ex_tfl, 1), "bound": "fp32 FFMA",
+                      "fp32_ffma_peak_tflops": 72.0, "frac_of_fp32_ffma_peak": round(ex_tfl / 72.0, 3)})
+    except Exception as ex:
+        lines.append({"case": "exact fp32 FFMA kernel", "error": f"{type(ex).__name__}: {str(ex)[:120]}"})
     saved = item_tab.clone()
     try:
         nd = n_items // 100

@@ -555,10 +555,11 @@ int launch_spmm(const SpmmArgs& a) {
             // rows per warp so that the grid still covers the SMs (CiteULike-shaped, 22.5k rows: 22 -> 88 CTAs)
             const bool big = a.n_rows >= (int64_t)148 * 24 * 128 || getenv("CR_SPMM_FORCE_BIG");   // (test knob: wide geometry on small graphs)
             const int rows_per_warp = big ? 128 : 32;
-            // Work-balanced ranges pay where a fixed 128 rows per warp leaves few, uneven warps — the row block of a 4- or 8-way
-            // partition (r02, 8 GPUs: 11.3 -> 8.8 ms per propagation).  On the whole 11M-row graph (86k warps, 18 waves) the fixed
-            // mapping is ~1 % faster (29.9 vs 30.2 ms, one box), so it stays there: balanced below 8 waves of fixed warps.
-            const bool few_warps = a.n_rows < (int64_t)148 * 4 * 8 * 8 * 128;
+            // Work-balanced ranges pay where a fixed 128 rows per warp leaves few, uneven warps: the row block of an 8-way
+            // partition (2.3 waves of CTAs; r02, 8 GPUs: 11.3 -> 8.8 ms per propagation).  With 4.5 waves (4-way partition) the
+            // fixed mapping is ahead again (10.4 vs 10.9 ms, same box, `profiles/r02_prop_probe_n4.jsonl`), and on the whole
+            // 11M-row graph (18 waves) by ~1 % (29.9 vs 30.2 ms): balanced below 4 waves of fixed warps only.
+            const bool few_warps = a.n_rows < (int64_t)148 * 4 * 8 * 4 * 128;
             const char* force = getenv("CR_SPMM_FIXED_ROWS");          // (A/B knob: 1 = always fixed, 0 = always balanced)
             const bool balanced = big && (force ? force[0] == '0' : few_warps);
             const int32_t* warp_rows = balanced ? a.warp_rows : nullptr;

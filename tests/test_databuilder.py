@@ -135,3 +135,29 @@ def test_from_disk_reads_the_reference_layout_unchanged():
         ArrayDataBuilder.from_disk("syntiny", "both", root=root)
     with pytest.raises(FileNotFoundError):
         ArrayDataBuilder.from_disk("nosuch", "item", root=root)
+
+
+def test_mask_rows_remap_for_compacted_tables():
+    """FullRankScorer._mask_in_rows_of: the train-mask CSR re-expressed in row numbers of a compacted item table — entries whose
+    item was compacted away are dropped, the others become their row number, per-row order kept, memoised per (plan, selection)."""
+    import torch
+    from coldrec_b200.scoring import EvalPlan, FullRankScorer
+    rng = np.random.default_rng(3)
+    n_items, n_q = 500, 40
+    rows = [np.sort(rng.choice(n_items, int(rng.integers(0, 30)), replace=False)) for _ in range(n_q)]
+    rows[5] = np.zeros(0, dtype=np.int64)
+    rowptr = np.zeros(n_q + 1, dtype=np.int64); np.cumsum([len(r) for r in rows], out=rowptr[1:])
+    col = np.concatenate(rows).astype(np.int32)
+    plan = EvalPlan(None, torch.arange(n_q, dtype=torch.int32), torch.from_numpy(rowptr), torch.from_numpy(col), torch.zeros(n_q + 1, dtype=torch.int64),
+                    torch.zeros(0, dtype=torch.int32), 1)
+    keep = rng.random(n_items) < 0.6
+    gids = torch.from_numpy(np.nonzero(keep)[0].astype(np.int32))
+    sc = FullRankScorer.__new__(FullRankScorer)
+    sc._remap_cache = {}
+    rp, c = sc._mask_in_rows_of(plan, gids, "k")
+    pos_of = {int(g): j for j, g in enumerate(gids.tolist())}
+    for j in range(n_q):
+        want = [pos_of[int(g)] for g in rows[j] if int(g) in pos_of]
+        assert c[int(rp[j]):int(rp[j + 1])].tolist() == want
+    assert sc._mask_in_rows_of(plan, gids, "k")[1] is c            # memoised
+    assert sc._mask_in_rows_of(plan, gids, "other")[1] is not c
