@@ -649,9 +649,17 @@ __global__ void __launch_bounds__(kThreads, 1) score_sweep_tc_kernel(const __gri
                     }
                 }
                 float m = max32(r);
-                if (seeding) {      // (warp-uniform) seed mode: this query's best score over the chunks free of masked items
+                if (seeding) {      // (warp-uniform) seed mode: this query's best UNMASKED score of the tile
                     const uint32_t bad = sMask[(ms * kChunks + c) * kBM + ulocal] | sCommon[ms * kChunks + c];
+#ifndef CR_TC_SEED_MASKED_MAX
                     if (bad) m = -CUDART_INF_F;      // a chunk holding a masked item is skipped: the bound stays valid, barely weaker
+#else                                            // (A/B knob) seed from the unmasked columns of such a chunk instead.  r02, one box:
+                    if (bad) {                   // +1-4 % on the in-kernel warm / cold settings, -1 % on the unflagged headline case
+                        m = -CUDART_INF_F;       // (136 more instructions next to the hot loop) — not worth it, off by default
+#pragma unroll
+                        for (int x = 0; x < 32; ++x) m = ((bad >> x) & 1u) ? m : fmaxf(m, __uint_as_float(r[x]));
+                    }
+#endif
                     tmax = fmaxf(tmax, m);
                 }
                 unsigned ev = __ballot_sync(CR_FULL_MASK, m > thr);

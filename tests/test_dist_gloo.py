@@ -270,7 +270,12 @@ def _grid_worker(rank, world, port, ret):
             b, e = sc.item_range(c["n_items"])
             s, i = sc.topk(Ut, It[b:e], b, plan)
             lo, hi = sc.user_slice(plan.n_q)
-            out[S] = dict(s=s.numpy(), i=i.numpy(), lo=lo, hi=hi, perf=sc.metrics(i, plan, [10, 20], rounded=False), items=(b, e))
+            # a host pipeline hands each rank only its user group's rows of the plan (HostBatchEvaluator): same lists, same metrics
+            g_lo, g_hi = sc.group_slice(plan.n_q)
+            s_g, i_g = sc.topk(Ut, It[b:e], b, plan.slice(g_lo, g_hi), n_q_total=plan.n_q)
+            assert torch.equal(i_g, i) and torch.equal(s_g, s)
+            perf_g = sc.metrics(i_g, plan.slice(g_lo, g_hi), [10, 20], rounded=False, n_q_total=plan.n_q)
+            out[S] = dict(s=s.numpy(), i=i.numpy(), lo=lo, hi=hi, perf=sc.metrics(i, plan, [10, 20], rounded=False), items=(b, e), perf_g=perf_g)
         ret[rank] = out
     finally:
         dist.destroy_process_group()
@@ -298,7 +303,7 @@ def test_grid_sharded_scoring(world):
             o = ret[r][S]
             assert np.array_equal(o["i"], ti[o["lo"]:o["hi"]]), f"S={S} rank {r}: ids differ from the single sweep"
             assert np.allclose(o["s"], ts[o["lo"]:o["hi"]], atol=1e-6)
-            assert np.allclose(o["perf"], want, atol=1e-9)
+            assert np.allclose(o["perf"], want, atol=1e-9) and np.allclose(o["perf_g"], want, atol=1e-9)
             seen[o["lo"]:o["hi"]] += 1
             assert o["items"][1] - o["items"][0] in (c["n_items"] // S, c["n_items"] // S + 1)
         assert (seen == 1).all(), f"S={S}: the user slices must tile the eval users"

@@ -524,3 +524,34 @@ def test_copy_rows_gather_scatter_and_errors():
     with pytest.raises(ValueError):
         ops.copy_rows(src, torch.zeros((80, 16), device=DEV))
     assert ops.copy_rows(src, dst, src_ids=si[:0].contiguous(), dst_ids=di[:0].contiguous()) is dst
+
+
+def test_host_batch_evaluator_stages_group_and_prefetches():
+    """HostBatchEvaluator (the e2e arm of bench.py): pinned host plans in, top-K + metric strings out; the plan of step k+1 is
+    copied on a copy stream while step k is swept.  Every step must equal ranking the same plan from device memory."""
+    from coldrec_b200 import ops
+    from coldrec_b200.dist import GridShardedFullRankScorer
+    from coldrec_b200.scoring import EvalPlan, HostBatchEvaluator
+    U, I, _, _, _, _ = _synthetic_scoring_case(77, 3000, 20000, 10, 64, 10)
+    Ud, Id = cu(U), cu(I)
+    rng = np.random.default_rng(8)
+    n_q = 700
+    plans = []
+    for step in range(5):
+        uids = rng.choice(3000, n_q, replace=False).astype(np.int32)
+        rows = [np.sort(rng.choice(20000, int(rng.integers(0, 40)), replace=False)) for _ in range(n_q)]
+        rp = np.zeros(n_q + 1, dtype=np.int64); np.cumsum([len(r) for r in rows], out=rp[1:])
+        gt = [np.sort(rng.choice(20000, 4, replace=False)) for _ in range(n_q)]
+        plans.append(dict(user_ids=torch.from_numpy(uids), mask_rowptr=torch.from_numpy(rp), mask_col=torch.from_numpy(np.concatenate(rows).astype(np.int32)),
+                          gt_rowptr=torch.arange(0, 4 * n_q + 1, 4, dtype=torch.int64), gt_col=torch.from_numpy(np.concatenate(gt).astype(np.int32))))
+    sc = GridShardedFullRankScorer(20, 1, ops.SCORE_TF32_CHECKED)
+    hb = HostBatchEvaluator(sc, [10, 20], n_q, n_q * 40, n_q * 4, torch.device(DEV))
+    pinned = [hb.pin(p) for p in plans]
+    for k, hp in enumerate(pinned):
+        perf = hb.run(Ud, Id, 0, hp, pinned[k + 1] if k + 1 < len(pinned) else None)
+        torch.cuda.synchronize()
+        dplan = EvalPlan.from_arrays(**{n: cu(v) for n, v in plans[k].items()})
+        s, i = sc.topk(Ud, Id, 0, dplan)
+        assert np.array_equal(hb.out_ids.numpy(), i.cpu().numpy()) and np.array_equal(hb.out_scores.numpy(), s.cpu().numpy()), f"step {k}"
+        assert perf == sc.metrics(i, dplan, [10, 20], rounded=True)
+        assert hb.h2d_bytes == sum(v.numel() * v.element_size() for v in hp.values())
