@@ -57,8 +57,10 @@ def parse():
     ap.add_argument("--shard", default="auto", choices=["auto", "items", "users"],
                     help="N>1 scoring layout.  items: the catalogue split N ways + NCCL candidate all-gather (north star).  auto "
                          "(default): the same, but item shards are kept at >= --min-shard-items items; beyond that the ranks form "
-                         "user groups (N=8: four 2.5M-item shards x two user groups).  users: item table replicated, no exchange")
-    ap.add_argument("--min-shard-items", type=int, default=2_500_000)
+                         "user groups (N=8: two 5M-item shards x four user groups).  users: item table replicated, no exchange")
+    ap.add_argument("--min-shard-items", type=int, default=5_000_000,
+                    help="--shard auto keeps item shards at least this long (the sweep runs at 0.94 of the tensor peak on 5M-item "
+                         "shards, 0.90 on 2.5M, 0.81 on 1.25M): N = 2, 4, 8 -> 2 item shards x N/2 user groups")
     ap.add_argument("--prop-result", default="full", choices=["full", "users"],
                     help="multi-GPU propagation result: the whole table on every GPU (as at N=1), or user rows replicated + item rows "
                          "with their owner (what item-sharded scoring consumes)")
