@@ -381,7 +381,8 @@ def run_lightgcn(args, device, rank, world, pk, pk_src, lib):
     exchange = None
     if world == 1:
         G.plan(D)
-        run = lambda: cr.propagate(G, E0u, E0i, LAYERS)
+        bufs = cr.PropagationBuffers(n_users + n_items, D, device, with_ego=True)     # no allocation inside the timed loop
+        run = lambda: cr.propagate(G, E0u, E0i, LAYERS, buffers=bufs)
         nnz_local = G.nnz
     else:
         from coldrec_b200.dist import RowPartitionedGraph

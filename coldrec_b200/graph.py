@@ -103,9 +103,11 @@ class PropagationBuffers:
     """Scratch of one propagation over an (N, d) table: the layer-mean accumulator and two ping-pong layer tables.
     Reusing one instance across calls (training steps, epochs) keeps the hot loop free of allocations."""
 
-    def __init__(self, n: int, d: int, device):
+    def __init__(self, n: int, d: int, device, with_ego: bool = False):
         self.acc = torch.empty((n, d), dtype=torch.float32, device=device)
         self.ping = [torch.empty((n, d), dtype=torch.float32, device=device) for _ in range(2)]
+        # room for the [U; I] concatenation of ``propagate`` (the torch.cat of LGCN_Encoder.forward, model/LightGCN.py:87)
+        self.ego = torch.empty((n, d), dtype=torch.float32, device=device) if with_ego else None
 
 
 def propagate_table(graph: CsrGraph, ego: torch.Tensor, n_layers: int, include_ego: bool = True, return_layers: bool = False,
@@ -139,7 +141,7 @@ def propagate_table(graph: CsrGraph, ego: torch.Tensor, n_layers: int, include_e
 
 
 def propagate(graph: CsrGraph, user_emb: torch.Tensor, item_emb: torch.Tensor, n_layers: int, include_ego: bool = True,
-              return_layers: bool = False):
+              return_layers: bool = False, buffers: Optional[PropagationBuffers] = None):
     """E0 = [U; I];  E_{k+1} = A.E_k;  result = mean over layers 0..L (LightGCN, model/LightGCN.py:86-96)
     or 1..L (``include_ego=False``: SimGCL/XSimGCL eval path, model/SimGCL.py:101-113).
 
@@ -148,11 +150,14 @@ def propagate(graph: CsrGraph, user_emb: torch.Tensor, item_emb: torch.Tensor, n
     [E_0 (if include_ego), E_1, ..., E_L] like NCL's encoder (model/NCL.py:186-196).
     """
     n_u = user_emb.shape[0]
-    ego = torch.cat([user_emb, item_emb], 0).contiguous()
+    if buffers is not None and buffers.ego is not None:      # allocation-free call (a trainer evaluates every epoch: 4 x (N, d) otherwise);
+        ego = torch.cat([user_emb, item_emb], 0, out=buffers.ego)       # the result is then a view of buffers.acc, valid until the next call
+    else:
+        ego = torch.cat([user_emb, item_emb], 0).contiguous()
     if return_layers:
-        acc, layers = propagate_table(graph, ego, n_layers, include_ego, True)
+        acc, layers = propagate_table(graph, ego, n_layers, include_ego, True, buffers=buffers)
         return acc[:n_u], acc[n_u:], layers
-    acc = propagate_table(graph, ego, n_layers, include_ego)
+    acc = propagate_table(graph, ego, n_layers, include_ego, buffers=buffers)
     return acc[:n_u], acc[n_u:]
 
 
