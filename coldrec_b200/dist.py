@@ -214,8 +214,11 @@ class ShardedItemGenerator:
         self.item_begin, self.item_end = scorer.item_range(n_items) if hasattr(scorer, "item_range") else \
             shard_range(n_items, scorer.rank, scorer.world)
 
-    def rows(self, table: torch.Tensor) -> torch.Tensor:
-        """This rank's rows of a full (n_items, *) table; a table that already has shard length is taken as the shard."""
+    def rows(self, table):
+        """This rank's rows of a full (n_items, *) table; a table that already has shard length is taken as the shard.  A
+        ``towers.prepare``d table (``ops.SplitTable``) is sliced half by half."""
+        if isinstance(table, ops.SplitTable):
+            return ops.SplitTable(self.rows(table.hi), self.rows(table.lo), table.width)
         if table.shape[0] == self.item_end - self.item_begin and table.shape[0] != self.n_items:
             return table
         if table.shape[0] != self.n_items:
@@ -223,7 +226,7 @@ class ShardedItemGenerator:
         return table[self.item_begin:self.item_end]
 
     def generate(self, fn: Callable, *row_tables: torch.Tensor) -> torch.Tensor:
-        out = fn(*[self.rows(t).contiguous() for t in row_tables])
+        out = fn(*[(lambda r: r if isinstance(r, ops.SplitTable) else r.contiguous())(self.rows(t)) for t in row_tables])
         if out.shape[0] != self.item_end - self.item_begin:
             raise ValueError("the generator must return one row per item of the shard")
         return out

@@ -150,7 +150,9 @@ class FullRankScorer:
         Memoised per (plan, selection): plans are memoised per eval set, the selection is a function of the flag bytes."""
         ck = (id(plan), key)
         hit = self._remap_cache.get(ck)
-        if hit is None or hit[0] is not plan:
+        # an entry is valid only for the very plan and kept-id tensors it was built from (both kept alive by the entry, so neither
+        # identity can be recycled): a rebuilt id list — new flags — can never meet an old remap
+        if hit is None or hit[0] is not plan or hit[3] is not gids:
             col = plan.mask_col
             pos = torch.searchsorted(gids, col)
             valid = gids[pos.clamp(max=gids.numel() - 1)] == col
@@ -160,7 +162,7 @@ class FullRankScorer:
             rowptr[1:] = torch.cumsum(torch.bincount(rowid[valid], minlength=plan.n_q), 0)
             if len(self._remap_cache) >= 16:
                 self._remap_cache.clear()
-            hit = (plan, rowptr, pos[valid].to(torch.int32).contiguous())
+            hit = (plan, rowptr, pos[valid].to(torch.int32).contiguous(), gids)
             self._remap_cache[ck] = hit
         return hit[1], hit[2]
 
@@ -195,7 +197,7 @@ class FullRankScorer:
                 continue
             if gids is not None:       # compacted table: sweep it as a contiguous catalogue of row numbers, map the rows back to ids
                 if plan.mask_col.numel():
-                    mrp, mcol = self._mask_in_rows_of(plan, gids, (item_flags.data_ptr(), item_flags._version, sel))
+                    mrp, mcol = self._mask_in_rows_of(plan, gids, sel)
                 else:
                     mrp, mcol = plan.mask_rowptr, plan.mask_col
                 s, i, nref = ops.score_topk(user_tab, tab, K, user_ids=plan.user_ids, mask_rowptr=mrp, mask_col=mcol, precision=self.precision)

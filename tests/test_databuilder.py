@@ -161,3 +161,6 @@ def test_mask_rows_remap_for_compacted_tables():
         assert c[int(rp[j]):int(rp[j + 1])].tolist() == want
     assert sc._mask_in_rows_of(plan, gids, "k")[1] is c            # memoised
     assert sc._mask_in_rows_of(plan, gids, "other")[1] is not c
+    gids2 = gids[:-3].clone()                                       # a rebuilt id list (new flags) under the same key: never the old remap
+    rp2, c2 = sc._mask_in_rows_of(plan, gids2, "k")
+    assert c2 is not c and int(c2.max()) < gids2.numel()
