@@ -108,9 +108,16 @@ def _golden_graph():
 def test_lightgcn_propagate_vs_reference_golden(L):
     from coldrec_b200 import CsrGraph, propagate
     g, A = _golden_graph()
-    u, i = propagate(CsrGraph.from_scipy(A, DEV), cu(g["E0_user"]), cu(g["E0_item"]), L)
+    G = CsrGraph.from_scipy(A, DEV)
+    u, i = propagate(G, cu(g["E0_user"]), cu(g["E0_item"]), L)
     assert_normwise(u, g[f"lgcn_L{L}_user"])
     assert_normwise(i, g[f"lgcn_L{L}_item"])
+    # allocation-free form (a trainer evaluates every epoch): same bits, results are views of the caller's buffers
+    from coldrec_b200 import PropagationBuffers
+    bufs = PropagationBuffers(A.shape[0], 64, DEV, with_ego=True)
+    for _ in range(2):
+        u2, i2 = propagate(G, cu(g["E0_user"]), cu(g["E0_item"]), L, buffers=bufs)
+        assert torch.equal(u2, u) and torch.equal(i2, i) and u2.data_ptr() == bufs.acc.data_ptr()
 
 
 def test_simgcl_ngcf_and_layer_list_vs_reference_golden():
