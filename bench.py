@@ -152,7 +152,7 @@ def ncu_traffic(key, src):
         return None, f"no committed ncu capture of {key}"
     sha = hashlib.sha256(open(os.path.join(ROOT, "coldrec_b200", "csrc", src), "rb").read()).hexdigest()
     if rec.get("source_sha256") != sha:
-        return None, f"stale: the committed capture was taken on another revision of csrc/{src} — re-capture (tools/gpu_prof.sh)"
+        return None, f"stale: the committed capture was taken on another revision of csrc/{src} — re-capture (tools/gpu_round_check.sh + tools/ncu_traffic.py)"
     return rec["bytes_per_launch"], None
 
 
