@@ -256,7 +256,8 @@ def run_config(key, device, lib, steps=5, warmup=2, cpu=True, host_threads=None)
         dn, ht = _tower_states(c, 11)
         dnd = {k: v.to(device) for k, v in dn.items() if v.dtype == torch.float32}
         htd = {k: v.to(device) for k, v in ht.items()}
-        Ud, Vd, Cd = U.to(device), V.to(device), content.to(device)
+        Ud, Vd = U.to(device), V.to(device)
+        Cd = towers.prepare(content.to(device))       # the constant content table in the layer kernel's operand form, once (as a trainer would)
 
         def step():
             n = 0

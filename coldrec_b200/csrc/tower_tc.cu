@@ -11,6 +11,12 @@
 // rounding of lo are ~2^-21 relative — the "3xTF32" scheme; measured against the reference towers it stays at a few 1e-7.
 // The split of a constant table (item content: 20,519 x 2,738 at XING shape) is done once (cr_split_tf32) and reused;
 // a layer's epilogue can emit its output already split, so a tower chain never runs a separate split pass in between.
+// "Raw" mode (X1lo == NULL) takes plain fp32 rows instead: TMA stages the fp32 tile and the four epilogue warps rewrite it in
+// shared memory as hi (in place) + lo (second buffer) between accumulator drains, fence it towards the async proxy and hand
+// the stage to the MMA warp — one HBM read of X instead of two.  Bit-identical results, but MEASURED SLOWER where it was meant
+// to help (XING content layer 0.31 vs 0.26 ms, kNN 4.2 vs 3.0 ms: 48 KB of extra shared-memory traffic per chunk sits on the
+// MMA's critical path); it wins only on short-K layers with wide outputs, where it saves two output tables.  towers.py uses
+// pre-split operands; the mode stays for callers that cannot keep a split copy.
 //
 // Accumulation.  The tensor core adds each MMA's result to the TMEM accumulator with truncation, not round-to-nearest: over the
 // 1056 MMAs of a K = 2,802 layer that bias reached 1.7e-5 (r02, first version: one accumulator for the whole K loop) — more
@@ -135,7 +141,7 @@ struct TowerTcParams {
     int row_blocks, col_blocks, col_fastest;   // 1-D grid of row_blocks x col_blocks CTAs; which index runs fastest (see the launch)
 };
 
-template <int NB>
+template <int NB, bool RAW>
 __global__ void __launch_bounds__(kThreads, 1)
 tower_layer_tc_kernel(const __grid_constant__ CUtensorMap mapA1h, const __grid_constant__ CUtensorMap mapA1l,
                       const __grid_constant__ CUtensorMap mapA2h, const __grid_constant__ CUtensorMap mapA2l,
@@ -149,7 +155,8 @@ tower_layer_tc_kernel(const __grid_constant__ CUtensorMap mapA1h, const __grid_c
     uint64_t* empty = bars + kMaxStages;       // [stages] MMA -> TMA
     uint64_t* tfull = bars + 2 * kMaxStages;   // [2] MMA -> epilogue: a K block is complete in accumulator stage a
     uint64_t* tempty = tfull + 2;              // [2] epilogue -> MMA: stage a has been drained
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* conv = tempty + 2;               // [stages] RAW: epilogue warps -> MMA: the stage's A tile has been split into hi / lo
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv + kMaxStages);
     const int warp = __shfl_sync(CR_FULL_MASK, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     const int row_blk = p.col_fastest ? (int)(blockIdx.x / p.col_blocks) : (int)(blockIdx.x % p.row_blocks);
@@ -160,7 +167,7 @@ tower_layer_tc_kernel(const __grid_constant__ CUtensorMap mapA1h, const __grid_c
     const int n_blocks = (n_chunks + kBlockChunks - 1) / kBlockChunks;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 4); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -180,11 +187,11 @@ tower_layer_tc_kernel(const __grid_constant__ CUtensorMap mapA1h, const __grid_c
                 const int s = c % p.stages;
                 if (c >= p.stages) mbar_wait(&empty[s], ((c / p.stages) - 1) & 1);
                 unsigned char* st = smem + (size_t)s * stage_bytes;
-                mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+                mbar_expect_tx(&full[s], (uint32_t)(RAW ? stage_bytes - kABytes : stage_bytes));
                 const bool seg2 = c >= p.chunks1;
                 const int kk = (seg2 ? c - p.chunks1 : c) * kBK;
-                tma_load_2d(st, seg2 ? &mapA2h : &mapA1h, &full[s], kk, (int)m0);
-                tma_load_2d(st + kABytes, seg2 ? &mapA2l : &mapA1l, &full[s], kk, (int)m0);
+                tma_load_2d(st, seg2 ? &mapA2h : &mapA1h, &full[s], kk, (int)m0);          // RAW: the fp32 tile itself
+                if constexpr (!RAW) tma_load_2d(st + kABytes, seg2 ? &mapA2l : &mapA1l, &full[s], kk, (int)m0);
                 const int wcol = seg2 ? p.d1 + kk : kk;
                 tma_load_2d(st + 2 * kABytes, &mapWh, &full[s], wcol, n0);
                 tma_load_2d(st + 2 * kABytes + b_bytes, &mapWl, &full[s], wcol, n0);
@@ -196,7 +203,7 @@ tower_layer_tc_kernel(const __grid_constant__ CUtensorMap mapA1h, const __grid_c
             const int s = c % p.stages, blk = c / kBlockChunks, a = blk & 1;
             const bool first = c % kBlockChunks == 0, last = (c % kBlockChunks == kBlockChunks - 1) || c == n_chunks - 1;
             if (first && blk >= 2) mbar_wait(&tempty[a], ((blk >> 1) - 1) & 1);
-            mbar_wait(&full[s], (c / p.stages) & 1);
+            mbar_wait(RAW ? &conv[s] : &full[s], (c / p.stages) & 1);      // RAW: the converters waited for the TMA bytes of the stage
             tc_fence_after();
             if (leader) {
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
@@ -222,7 +229,30 @@ tower_layer_tc_kernel(const __grid_constant__ CUtensorMap mapA1h, const __grid_c
         float run[NB];
 #pragma unroll
         for (int x = 0; x < NB; ++x) run[x] = 0.f;
+        [[maybe_unused]] int cconv = 0;            // RAW: next chunk whose A tile these warps split
+        [[maybe_unused]] const int et = (quad * 32 + lane);
         for (int blk = 0; blk < n_blocks; ++blk) {
+            if constexpr (RAW) {
+                // stay one K block ahead of the drain: the MMA warp works on block blk + 1 while block blk is drained
+                const int upto = min(n_chunks, (blk + 2) * kBlockChunks);
+                for (; cconv < upto; ++cconv) {
+                    const int s = cconv % p.stages;
+                    mbar_wait(&full[s], (cconv / p.stages) & 1);
+                    float4* hi4 = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+                    float4* lo4 = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + kABytes);
+#pragma unroll
+                    for (int j = 0; j < kABytes / 16 / 128; ++j) {       // elementwise: the swizzled layout is the same for hi and lo
+                        const float4 x = hi4[j * 128 + et];
+                        float4 h;
+                        h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
+                        hi4[j * 128 + et] = h;
+                        lo4[j * 128 + et] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to tcgen05.mma
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&conv[s]);
+                }
+            }
             const int a = blk & 1;
             mbar_wait(&tfull[a], (blk >> 1) & 1);
             tc_fence_after();
@@ -372,13 +402,15 @@ int cr_linear_act_tc_f32(const float* X1hi, const float* X1lo, int64_t ld1, int 
                          int d2, int64_t n_rows, const float* Whi, const float* Wlo, int64_t ldw, const float* bias, const float* scale,
                          const float* shift, int n_out, int act, float* Y, int64_t ldy, const int32_t* yrow, float* Yhi, float* Ylo,
                          int64_t ldh, void* stream) {
-    if (!X1hi || !X1lo || !Whi || !Wlo || n_rows < 0 || d1 <= 0 || d2 < 0 || (d2 > 0 && (!X2hi || !X2lo)) || n_out <= 0) return CR_ERR_ARG;
+    const bool raw = X1lo == nullptr;          // plain fp32 rows, split inside the kernel (both segments alike)
+    if (!X1hi || !Whi || !Wlo || n_rows < 0 || d1 <= 0 || d2 < 0 || (d2 > 0 && !X2hi) || n_out <= 0) return CR_ERR_ARG;
+    if (d2 > 0 && ((X2lo == nullptr) != raw)) return CR_ERR_ARG;
     if ((!Y && !Yhi) || ((Yhi == nullptr) != (Ylo == nullptr)) || (Y && ldy < n_out) || (Yhi && ldh < n_out)) return CR_ERR_ARG;
     if (((scale == nullptr) != (shift == nullptr)) || ldw < d1 + d2 || ld1 < d1 || (d2 > 0 && ld2 < d2)) return CR_ERR_ARG;
     if (act < CR_ACT_NONE || act > CR_ACT_LEAKY_RELU || n_rows > 0x7fffffffLL) return CR_ERR_UNSUPPORTED;
     if (yrow && Yhi) return CR_ERR_UNSUPPORTED;       // split outputs are written in input row order
-    if (!tma_ok(X1hi, ld1) || !tma_ok(X1lo, ld1) || !tma_ok(Whi, ldw) || !tma_ok(Wlo, ldw)) return CR_ERR_ALIGN;
-    if (d2 > 0 && (!tma_ok(X2hi, ld2) || !tma_ok(X2lo, ld2))) return CR_ERR_ALIGN;
+    if (!tma_ok(X1hi, ld1) || (!raw && !tma_ok(X1lo, ld1)) || !tma_ok(Whi, ldw) || !tma_ok(Wlo, ldw)) return CR_ERR_ALIGN;
+    if (d2 > 0 && (!tma_ok(X2hi, ld2) || (!raw && !tma_ok(X2lo, ld2)))) return CR_ERR_ALIGN;
     int rc = cr::require_device();
     if (rc != CR_OK) return rc;
     if (n_rows == 0) return CR_OK;
@@ -395,10 +427,12 @@ int cr_linear_act_tc_f32(const float* X1hi, const float* X1lo, int64_t ld1, int 
     const int smem = p.stages * stage_bytes + 1024;
     CUtensorMap a1h, a1l, a2h, a2l, wh, wl;
     if ((rc = make_map(&a1h, X1hi, n_rows, d1, ld1, kBM)) != CR_OK) return rc;
-    if ((rc = make_map(&a1l, X1lo, n_rows, d1, ld1, kBM)) != CR_OK) return rc;
+    if (raw) a1l = a1h;
+    else if ((rc = make_map(&a1l, X1lo, n_rows, d1, ld1, kBM)) != CR_OK) return rc;
     if (d2 > 0) {
         if ((rc = make_map(&a2h, X2hi, n_rows, d2, ld2, kBM)) != CR_OK) return rc;
-        if ((rc = make_map(&a2l, X2lo, n_rows, d2, ld2, kBM)) != CR_OK) return rc;
+        if (raw) a2l = a2h;
+        else if ((rc = make_map(&a2l, X2lo, n_rows, d2, ld2, kBM)) != CR_OK) return rc;
     } else {
         a2h = a1h; a2l = a1l;
     }
@@ -410,17 +444,18 @@ int cr_linear_act_tc_f32(const float* X1hi, const float* X1lo, int64_t ld1, int 
     // (the query block of the kNN path, which fits L2) against a big W wants the row blocks side by side.
     p.row_blocks = (int)((n_rows + kBM - 1) / kBM);
     p.col_blocks = (n_out + NB - 1) / NB;
-    const double a_bytes = 2.0 * (double)n_rows * (d1 + d2) * 4.0;
+    const double a_bytes = (raw ? 1.0 : 2.0) * (double)n_rows * (d1 + d2) * 4.0;
     p.col_fastest = a_bytes > 96.0 * 1024 * 1024 ? 1 : 0;
     if ((int64_t)p.row_blocks * p.col_blocks > 0x7fffffffLL) return CR_ERR_UNSUPPORTED;
     const unsigned grid = (unsigned)((int64_t)p.row_blocks * p.col_blocks);
-    if (NB == 64) {
-        CR_CUDA_TRY(cudaFuncSetAttribute(tower_layer_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        tower_layer_tc_kernel<64><<<grid, kThreads, smem, (cudaStream_t)stream>>>(a1h, a1l, a2h, a2l, wh, wl, p);
-    } else {
-        CR_CUDA_TRY(cudaFuncSetAttribute(tower_layer_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        tower_layer_tc_kernel<128><<<grid, kThreads, smem, (cudaStream_t)stream>>>(a1h, a1l, a2h, a2l, wh, wl, p);
-    }
+#define CR_TOWER(NB_, RAW_)                                                                                                     \
+    do {                                                                                                                        \
+        CR_CUDA_TRY(cudaFuncSetAttribute(tower_layer_tc_kernel<NB_, RAW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)); \
+        tower_layer_tc_kernel<NB_, RAW_><<<grid, kThreads, smem, (cudaStream_t)stream>>>(a1h, a1l, a2h, a2l, wh, wl, p);        \
+    } while (0)
+    if (NB == 64) { if (raw) CR_TOWER(64, true); else CR_TOWER(64, false); }
+    else { if (raw) CR_TOWER(128, true); else CR_TOWER(128, false); }
+#undef CR_TOWER
     CR_LAUNCH_CHECK("tower_layer_tc_kernel");
     return CR_OK;
 }

@@ -61,7 +61,7 @@ def _knn_wide(q: torch.Tensor, v: torch.Tensor, k: int, exclude_self: bool, bloc
     out_i = torch.empty((n_q, k), dtype=torch.int32, device=q.device)
     for lo in range(0, n_q, rows):
         hi = min(n_q, lo + rows)
-        ops.linear_act_tc(ops.split_tf32(q[lo:hi]), vs, None, out=S[:hi - lo])
+        ops.linear_act_tc(ops.split_tf32(q[lo:hi]), vs, None, out=S[:hi - lo])     # (pre-split rows: 3.0 vs 4.2 ms with the in-kernel split, XING shape)
         ex = torch.arange(lo, hi, dtype=torch.int32, device=q.device) if exclude_self else None
         out_s[lo:hi], out_i[lo:hi] = ops.topk_rows(S[:hi - lo], k, exclude_col=ex)
     return out_s, out_i

@@ -14,7 +14,7 @@ import torch
 from . import _lib
 
 __all__ = ["spmm_plan", "spmm", "spmm_bcast", "score_topk", "topk_merge", "fill_masked", "gather_rows", "rank_metrics", "linear_act", "bn_fold",
-           "SplitTable", "split_tf32", "linear_act_tc", "topk_rows",
+           "SplitTable", "split_tf32", "tma_rows", "linear_act_tc", "topk_rows",
            "heater_blend", "bpr_fwd_bwd", "adam_step", "sample_pairwise", "SCORE_EXACT_F32", "SCORE_TF32_CHECKED"]
 
 SCORE_EXACT_F32 = _lib.SCORE_EXACT_F32
@@ -358,27 +358,60 @@ def split_tf32(x: torch.Tensor) -> SplitTable:
     return SplitTable(hi, lo, cols)
 
 
-def linear_act_tc(X1: SplitTable, W: SplitTable, bias=None, *, X2: Optional[SplitTable] = None, scale=None, shift=None, act=None,
+def tma_rows(x: torch.Tensor) -> torch.Tensor:
+    """``x`` as the tensor-core layer can read it directly: fp32, unit inner stride, 16-byte aligned rows (row stride a
+    multiple of 4 floats).  Returns ``x`` itself when it already qualifies, else a padded copy (a view of width ``x.shape[1]``
+    into a (rows, ld) buffer) — do it once for a constant table such as the item content (2,738 columns -> stride 2,740)."""
+    x = _req(x, torch.float32, "x", contiguous=False)
+    if x.dim() != 2:
+        raise ValueError("x must be 2-D")
+    if x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0:
+        return x
+    rows, cols = x.shape
+    ld = (cols + 3) // 4 * 4
+    buf = torch.zeros((rows, ld), dtype=torch.float32, device=x.device)
+    buf[:, :cols].copy_(x)
+    return buf[:, :cols]
+
+
+def linear_act_tc(X1, W: SplitTable, bias=None, *, X2=None, scale=None, shift=None, act=None,
                   out=None, yrow=None, want_split: bool = False, want_plain: bool = True):
-    """``linear_act`` on the tensor cores at fp32 accuracy (``cr_linear_act_tc_f32``: tcgen05 kind::tf32, hi.hi + lo.hi + hi.lo).
-    X1 / X2 / W are ``SplitTable``s (W = split of the nn.Linear weight [n_out, X1.width + X2.width]).  Returns
-    (out | None, SplitTable of the output | None) — with ``want_split`` the output is emitted already split for the next
-    layer.  Rows are contiguous (no gather); ``yrow`` scatters the rows of ``out`` (GAR.py:44-46)."""
+    """``linear_act`` on the tensor cores at fp32 accuracy (``cr_linear_act_tc_f32``: tcgen05 kind::tf32, hi.hi + lo.hi + hi.lo,
+    K blocks drained into fp32 running sums).  W is the ``SplitTable`` of the nn.Linear weight [n_out, k1 + k2].  X1 / X2 are
+    ``SplitTable``s (what towers.py passes: fastest) or plain fp32 tensors, split into hi + lo INSIDE the kernel (one HBM read,
+    bit-identical, measured ~15 % slower on wide-K layers).  Returns
+    (out | None, SplitTable of the output | None); rows are contiguous (no gather), ``yrow`` scatters the rows of ``out``
+    (GAR.py:44-46)."""
     lib = _lib.load()
-    tabs = [X1.hi, X1.lo, W.hi, W.lo] + ([X2.hi, X2.lo] if X2 is not None else [])
-    for t in tabs:
-        _req(t, torch.float32, "split table")
+    raw = not isinstance(X1, SplitTable)
+    if X2 is not None and isinstance(X2, SplitTable) == raw:       # mixed: bring both to the split form
+        X1, X2, raw = (X1 if isinstance(X1, SplitTable) else split_tf32(X1)), (X2 if isinstance(X2, SplitTable) else split_tf32(X2)), False
+    if raw:
+        X1 = tma_rows(X1)
+        X2 = None if X2 is None else tma_rows(X2)
+        x1h, x1l, ld1, d1, n_rows = X1, None, X1.stride(0) if X1.shape[0] > 1 else max(X1.stride(0), (X1.shape[1] + 3) // 4 * 4), X1.shape[1], X1.shape[0]
+        x2h, x2l, ld2, d2 = (None, None, 0, 0) if X2 is None else (X2, None, X2.stride(0) if X2.shape[0] > 1 else max(X2.stride(0), (X2.shape[1] + 3) // 4 * 4), X2.shape[1])
+        if X2 is not None and X2.shape[0] != n_rows:
+            raise ValueError("X1 and X2 differ in rows")
+        tabs = [t for t in (x1h, x2h) if t is not None]
+    else:
+        x1h, x1l, ld1, d1, n_rows = X1.hi, X1.lo, X1.hi.stride(0), X1.width, X1.rows
+        x2h, x2l, ld2, d2 = (None, None, 0, 0) if X2 is None else (X2.hi, X2.lo, X2.hi.stride(0), X2.width)
+        if X2 is not None and X2.rows != n_rows:
+            raise ValueError("X1 and X2 differ in rows")
+        tabs = [t for t in (x1h, x1l, x2h, x2l) if t is not None]
+        for t in tabs:
+            _req(t, torch.float32, "split table")
+    for t in (W.hi, W.lo):
+        _req(t, torch.float32, "W split table")
     bias = _req(bias, torch.float32, "bias", optional=True)
     scale = _req(scale, torch.float32, "scale", optional=True)
     shift = _req(shift, torch.float32, "shift", optional=True)
     yrow = _req(yrow, torch.int32, "yrow", optional=True)
-    dev = _same_device(*tabs, bias, scale, shift, yrow, out)
-    n_rows, n_out = X1.rows, W.rows
-    d1, d2 = X1.width, (0 if X2 is None else X2.width)
+    dev = _same_device(*tabs, W.hi, W.lo, bias, scale, shift, yrow, out)
+    n_out = W.rows
     if W.width != d1 + d2:
         raise ValueError(f"W has {W.width} columns, inputs give k={d1 + d2}")
-    if X2 is not None and X2.rows != n_rows:
-        raise ValueError("X1 and X2 differ in rows")
     if act not in _ACTS:
         raise ValueError(f"unknown activation {act!r}")
     if out is None and want_plain:
@@ -394,8 +427,7 @@ def linear_act_tc(X1: SplitTable, W: SplitTable, bias=None, *, X2: Optional[Spli
     if n_rows == 0:
         return out, sp
     with torch.cuda.device(dev):
-        rc = lib.cr_linear_act_tc_f32(_ptr(X1.hi), _ptr(X1.lo), X1.hi.stride(0), d1, _ptr(None if X2 is None else X2.hi),
-                                      _ptr(None if X2 is None else X2.lo), 0 if X2 is None else X2.hi.stride(0), d2, n_rows,
+        rc = lib.cr_linear_act_tc_f32(_ptr(x1h), _ptr(x1l), ld1, d1, _ptr(x2h), _ptr(x2l), ld2, d2, n_rows,
                                       _ptr(W.hi), _ptr(W.lo), W.hi.stride(0), _ptr(bias), _ptr(scale), _ptr(shift), n_out, _ACTS[act],
                                       _ptr(out), 0 if out is None else out.stride(0), _ptr(yrow), _ptr(None if sp is None else sp.hi),
                                       _ptr(None if sp is None else sp.lo), 0 if sp is None else sp.hi.stride(0), _stream(dev))

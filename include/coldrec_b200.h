@@ -193,6 +193,8 @@ CR_API int cr_linear_act_f32(const float *X1, int64_t ld1, int d1, const float *
  * Rows are contiguous (no xrow gather); X1/X2/W tables need 16-byte aligned bases and row strides (ld % 4 == 0);
  * n_out <= 256.  Outputs: Y (nullable, scattered through yrow if given) and/or the split (Yhi, Ylo) of the same values
  * with row stride ldh >= n_out (columns [n_out, ldh) are zeroed) — the next layer's input without a split pass.
+ * X1lo == NULL (and X2lo == NULL) = "raw" mode: X1hi / X2hi are plain fp32 rows, split hi + lo inside the kernel (one HBM
+ * read, bit-identical results; measured slower on wide-K layers, see tower_tc.cu).
  * Same replaced reference lines as cr_linear_act_f32. */
 CR_API int cr_linear_act_tc_f32(const float *X1hi, const float *X1lo, int64_t ld1, int d1, const float *X2hi, const float *X2lo,
                          int64_t ld2, int d2, int64_t n_rows, const float *Whi, const float *Wlo, int64_t ldw,

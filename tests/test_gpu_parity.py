@@ -458,6 +458,9 @@ def test_tower_layer_tc_3xtf32_matches_fp64(shape):
     hi, lo = sp.hi.cpu().numpy(), sp.lo.cpu().numpy()
     assert np.array_equal((hi.astype(np.float64) + lo)[:, :n_out].astype(np.float32), y.cpu().numpy())
     assert (hi.view(np.uint32) & 0x1FFF).max() == 0 and not hi[:, n_out:].any() and not lo[:, n_out:].any()
+    # raw fp32 rows, split inside the kernel (one HBM read): the same MMAs on the same hi / lo values -> the same bits
+    y_raw, _ = ops.linear_act_tc(cu(X1), ops.split_tf32(cu(W)), cu(b), X2=cu(X2) if d2 else None, scale=cu(sc), shift=cu(sh), act="tanh")
+    assert torch.equal(y_raw, y), "in-kernel split differs from the pre-split operands"
     # no epilogue, scattered rows
     perm = rng.permutation(n + 3)[:n].astype(np.int32)
     out = torch.full((n + 3, n_out), 7.0, device=DEV)

@@ -136,4 +136,7 @@ if what in ("towers", "all"):
     y3, sp = ops.linear_act_tc(ops.split_tf32(X2), ops.split_tf32(W), b, X2=ops.split_tf32(X), act="tanh", want_split=True)
     torch.cuda.synchronize()
     assert (y3 - ref).abs().max().item() < 1e-5
+    y4, _ = ops.linear_act_tc(X2, ops.split_tf32(W), b, X2=X, act="tanh")                 # raw rows: hi / lo split inside the kernel
+    torch.cuda.synchronize()
+    assert torch.equal(y4, y3)
     print("towers (SIMT + tcgen05 3xTF32): ok")
