@@ -21,6 +21,10 @@ class CsrGraph:
 
     ``n_cols`` is the number of rows of the gather source; for a row-partitioned graph ``n_rows`` is
     the local block and ``row_begin`` its first global row.
+
+    Single-stream object: the long-row plan cached per width (``plan(d)``) also holds the partial-sum scratch of the split
+    path, so two SpMMs on the SAME graph must not run concurrently on different streams (e.g. an eval-time propagate
+    overlapping a captured training step) — use one ``CsrGraph`` (one plan) per stream; the CSR arrays themselves can be shared.
     """
 
     def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], n_cols: int,

@@ -74,7 +74,9 @@ CR_API int cr_profile_read(int tag, double *total_ms, int *launches);
  * rowptr/Y/acc describe the caller's LOCAL row block (row-partitioned multi-GPU passes its slice);
  * X is the full gather source.  val == NULL means all-ones.  `plan` (from cr_spmm_plan) enables the
  * split path for rows longer than 512 nonzeros; plan == NULL processes every row with one warp.
- * A plan belongs to one (rowptr, nnz, d) triple and is reused across layers and epochs.
+ * A plan belongs to one (rowptr, nnz, d) triple and is reused across layers and epochs.  It also holds the partial-sum
+ * scratch of the split path and (round 2) the table of work-balanced warp row ranges: calls that share a plan must be
+ * ordered on one stream (one plan per stream otherwise).
  * ------------------------------------------------------------------------------------------------ */
 CR_API size_t cr_spmm_plan_bytes(int64_t n_rows, int64_t nnz, int d);
 CR_API int cr_spmm_plan(const int64_t *rowptr, int64_t n_rows, int64_t nnz, int d, void *plan, size_t plan_bytes,
