@@ -849,13 +849,16 @@ __global__ void item_bad_bits_kernel(const uint8_t* __restrict__ item_flags, uin
     if ((threadIdx.x & 31) == 0) bits[w] = b;
 }
 
+// dst[r, :] = [src[ids[r], 0:src_d] | 0 ...]: rows of width src_d (<= kD) gathered into kD-wide rows (zero columns do not change
+// an inner product: a 32-, 48- or 96-wide table is swept by the 64 / 128 instantiation)
 template <int kD>
-__global__ void gather_q_kernel(const float4* __restrict__ src, const int32_t* __restrict__ ids, int64_t n, float4* __restrict__ dst) {
+__global__ void gather_q_kernel(const float4* __restrict__ src, const int32_t* __restrict__ ids, int64_t n, int src_d4, float4* __restrict__ dst) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * (kD / 4)) return;
     const int64_t r = i / (kD / 4);
+    const int c = (int)(i % (kD / 4));
     const int64_t row = ids ? (int64_t)__ldg(ids + r) : r;
-    dst[i] = __ldg(src + row * (kD / 4) + (i % (kD / 4)));
+    dst[i] = c < src_d4 ? __ldg(src + row * src_d4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // Lists that came up short because masked items never become candidates here: append the first masked
@@ -920,10 +923,10 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows, int kD, int kBN)
 
 struct TcPlan {
     int ksel, cap, n_utiles, n_q_pad, n_tiles, S, tiles_per_split;
-    size_t off_q, off_buf, off_cnt, off_thr, off_norm, off_list, off_count, off_ps, off_pi, off_bits, off_exact, exact_bytes, total;
+    size_t off_q, off_buf, off_cnt, off_thr, off_norm, off_list, off_count, off_ps, off_pi, off_bits, off_pad, off_exact, exact_bytes, total;
 };
 
-TcPlan tc_plan(int64_t n_q, int64_t n_items, int K, int kD) {
+TcPlan tc_plan(int64_t n_q, int64_t n_items, int K, int kD, int src_d = 0) {
     const int kBN = kD == 64 ? Geo<64>::kBN : Geo<128>::kBN;
     TcPlan P{};
     P.ksel = (K <= 24) ? 32 : 64;
@@ -957,6 +960,7 @@ TcPlan tc_plan(int64_t n_q, int64_t n_items, int K, int kD) {
     P.off_ps = take((size_t)P.S * n_q * K * 4);
     P.off_pi = take((size_t)P.S * n_q * K * 4);
     P.off_bits = take((size_t)(P.n_tiles + 1) * (kBN / 32) * 4);      // "never take" words of the flag mask (tile-chunk granularity)
+    P.off_pad = take(src_d > 0 && src_d != kD ? (size_t)n_items * kD * 4 : 0);    // zero-padded copy of a narrower item table
     P.exact_bytes = cr::refine_workspace_bytes(K);
     P.off_exact = take(P.exact_bytes);
     P.total = off;
@@ -967,11 +971,13 @@ TcPlan tc_plan(int64_t n_q, int64_t n_items, int K, int kD) {
 
 namespace cr {
 
-static inline bool tc_width(int d) { return d == 64 || d == 128; }
+// widths served by the tensor-core sweep: 64 and 128 natively; any other multiple of 4 up to 128 zero-padded to the next of the two
+// (costs a padded copy of the item table in the workspace; d = 32 -> 64 doubles the FLOPs and still beats the FFMA kernel 25x)
+static inline int tc_width(int d) { return (d <= 0 || d > 128 || d % 4 != 0) ? 0 : (d <= 64 ? 64 : 128); }
 
 size_t tc_workspace_bytes(int64_t n_q, int64_t n_items, int d, int K) {
     if (!tc_width(d) || K > 52) return exact_workspace_bytes(n_q, n_items, K);
-    return tc_plan(n_q, n_items, K, d).total;
+    return tc_plan(n_q, n_items, K, tc_width(d), d).total;
 }
 
 template <int kD>
@@ -980,7 +986,7 @@ static int launch_tc_scorer_d(const ExactJob& j, int32_t* n_refined, void* ws, s
     const int64_t n_q = j.n_q, n_items = j.n_items;
     const int K = j.K;
     if (n_q == 0) return CR_OK;
-    const TcPlan P = tc_plan(n_q, n_items, K, kD);
+    const TcPlan P = tc_plan(n_q, n_items, K, kD, j.d);
     if (!ws || ws_bytes < P.total) return CR_ERR_WORKSPACE;
     if (!aligned16(ws)) return CR_ERR_ALIGN;
     char* base = (char*)ws;
@@ -994,18 +1000,26 @@ static int launch_tc_scorer_d(const ExactJob& j, int32_t* n_refined, void* ws, s
     float* part_s = (P.S > 1) ? (float*)(base + P.off_ps) : j.out_score;
     int32_t* part_i = (P.S > 1) ? (int32_t*)(base + P.off_pi) : j.out_id;
     const uint8_t* flags = j.flag_exclude ? j.item_flags : nullptr;
+    const float* item_tab = j.item_tab;
 
     CR_CUDA_TRY(cudaMemsetAsync(norm, 0, 256, st));
     CR_CUDA_TRY(cudaMemsetAsync(rcount, 0, 256, st));
     {
         const int64_t total = n_q * (kD / 4);
-        gather_q_kernel<kD><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float4*)j.user_tab, j.user_ids, n_q, (float4*)Q);
+        gather_q_kernel<kD><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float4*)j.user_tab, j.user_ids, n_q, j.d / 4, (float4*)Q);
         CR_LAUNCH_CHECK("gather_q_kernel");
-        item_norm_max_kernel<kD><<<148 * 4, 256, 0, st>>>((const float4*)j.item_tab, n_items, norm);
+        if (j.d != kD) {       // narrower table: zero-padded copy (the sweep, the rescoring and the norm bound read the copy)
+            const int64_t tot_i = n_items * (kD / 4);
+            gather_q_kernel<kD><<<(unsigned)((tot_i + 255) / 256), 256, 0, st>>>((const float4*)j.item_tab, nullptr, n_items, j.d / 4,
+                                                                                (float4*)(base + P.off_pad));
+            CR_LAUNCH_CHECK("gather_q_kernel");
+            item_tab = (const float*)(base + P.off_pad);
+        }
+        item_norm_max_kernel<kD><<<148 * 4, 256, 0, st>>>((const float4*)item_tab, n_items, norm);
         CR_LAUNCH_CHECK("item_norm_max_kernel");
     }
     CUtensorMap map_i;
-    int rc = make_map(&map_i, j.item_tab, n_items, kD, G::kBN);
+    int rc = make_map(&map_i, item_tab, n_items, kD, G::kBN);
     if (rc != CR_OK) return rc;
 
     SweepParams sp{};
@@ -1043,7 +1057,7 @@ static int launch_tc_scorer_d(const ExactJob& j, int32_t* n_refined, void* ws, s
     CR_LAUNCH_CHECK("score_sweep_tc_kernel");
     prof_stop(PROF_SCORE_SWEEP, st);
 
-    RescoreParams rp{Q, j.item_tab, j.item_gids, j.item_id_base, n_q, P.n_q_pad, P.S, K, P.cap, buf, cnt, thr, norm,
+    RescoreParams rp{Q, item_tab, j.item_gids, j.item_id_base, n_q, P.n_q_pad, P.S, K, P.cap, buf, cnt, thr, norm,
                      part_s, part_i, j.out_score, rlist, rcount};
     const int64_t warps = n_q * P.S;
     const unsigned rgrid = (unsigned)((warps * 32 + 255) / 256);
@@ -1077,8 +1091,8 @@ int launch_tc_scorer(const ExactJob& j, int32_t* n_refined, void* ws, size_t ws_
         // exact fp32 everywhere: a stricter result than TF32-checked asks for, never a weaker one
         return launch_exact_scorer(j, ws, ws_bytes, st);
     }
-    return j.d == 64 ? launch_tc_scorer_d<64>(j, n_refined, ws, ws_bytes, st, dbg_scores)
-                     : launch_tc_scorer_d<128>(j, n_refined, ws, ws_bytes, st, dbg_scores);
+    return tc_width(j.d) == 64 ? launch_tc_scorer_d<64>(j, n_refined, ws, ws_bytes, st, dbg_scores)
+                               : launch_tc_scorer_d<128>(j, n_refined, ws, ws_bytes, st, dbg_scores);
 }
 
 int read_tc_timeline(unsigned long long* host_out, int n_units) {

@@ -121,7 +121,9 @@ CR_API int cr_spmm_csr_bcast_f32(const int64_t *rowptr, const int32_t *col, cons
  * If fewer than K items exist the tail is padded with (-inf, -1).  With CR_SCORE_TF32_CHECKED the
  * selection runs on tcgen05 TF32 and every returned score is re-computed in fp32; queries whose
  * TF32 margin could not be proven are re-run exactly inside the same call, and their number is
- * written to *n_refined (device int32, nullable).
+ * written to *n_refined (device int32, nullable).  The tensor-core path serves K <= 52 and every width d <= 128 with
+ * d % 4 == 0: d = 64 and d = 128 natively (d = 128 = VBPR / AMR's concatenated tables, model/VBPR.py:68-75), other widths
+ * zero-padded to the next of the two inside the workspace; wider tables and K > 52 take the exact fp32 kernel.
  * ------------------------------------------------------------------------------------------------ */
 CR_API size_t cr_score_topk_workspace_bytes(int64_t n_q, int64_t n_items, int d, int K, int precision);
 CR_API int cr_score_topk_f32(const float *user_tab, const int32_t *user_ids, int64_t n_q, const float *item_tab,

@@ -313,7 +313,10 @@ def _synthetic_scoring_case(seed, n_users, n_items, n_q, d, mask_per_user, dup_f
 
 @pytest.mark.parametrize("precision", PRECISIONS, ids=["exact", "tf32"])
 @pytest.mark.parametrize("shape", [(500, 3000, 333, 64, 40, 0.0), (900, 20000, 700, 64, 120, 0.02), (300, 5000, 300, 128, 30, 0.0),
-                                   (64, 40, 64, 64, 10, 0.0), (200, 70000, 37, 64, 200, 0.01)])
+                                   (64, 40, 64, 64, 10, 0.0), (200, 70000, 37, 64, 200, 0.01),
+                                   # widths zero-padded onto the 64 / 128 tensor-core instantiations, and one beyond them (FFMA kernel)
+                                   (400, 9000, 300, 32, 30, 0.0), (300, 6000, 256, 96, 20, 0.01), (200, 4000, 150, 48, 10, 0.0),
+                                   (150, 3000, 100, 200, 10, 0.0)])
 def test_score_topk_vs_oracle_synthetic(shape, precision):
     from coldrec_b200 import ops
     n_users, n_items, n_q, d, mpu, dup = shape
