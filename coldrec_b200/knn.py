@@ -42,9 +42,8 @@ def knn_inner_product(query, value, k: int, device="cuda:0", exclude_self: bool 
     if exclude_self:
         rowptr = torch.arange(q.shape[0] + 1, dtype=torch.int64, device=q.device)
         col = torch.arange(q.shape[0], dtype=torch.int32, device=q.device)
-    # d = 64 / 128: the tcgen05 sweep (TF32-checked: exact fp32 scores of a proven top-k); other widths <= 128: exact fp32 kernel
-    s, i, _ = ops.score_topk(q, v, k, mask_rowptr=rowptr, mask_col=col,
-                             precision=ops.SCORE_TF32_CHECKED if q.shape[1] in (64, 128) else ops.SCORE_EXACT_F32)
+    # widths <= 128: the tcgen05 sweep (TF32-checked: exact fp32 scores of a proven top-k; narrower tables zero-padded to 64 / 128)
+    s, i, _ = ops.score_topk(q, v, k, mask_rowptr=rowptr, mask_col=col, precision=ops.SCORE_TF32_CHECKED)
     return s, i
 
 

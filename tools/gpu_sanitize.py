@@ -61,6 +61,7 @@ if what in ("sweep", "all"):
     sweep_case(400, 96 * 90, 200, 8, 0, compact=True)        # compacted table: per-entry binary search in the bitmap producer
     sweep_case(500, 64 * 90 + 5, 300, 10, 0, d=128)          # d = 128 instantiation (64-item tiles, four TMA boxes per tile)
     sweep_case(500, 64 * 1100, 260, 10, 128, with_flags=True, d=128)
+    sweep_case(300, 96 * 60 + 11, 200, 8, 0, d=48)            # narrower table: zero-padded copy in the workspace, d = 64 instantiation
     s, i, _ = ops.score_topk(torch.randn(64, 64, device=dev), torch.randn(5000, 64, device=dev), 20, precision=ops.SCORE_EXACT_F32)
     torch.cuda.synchronize()
     print("exact scorer: ok")
