@@ -65,3 +65,32 @@ def test_b200_arm_line_at_toy_sizes():
         assert "error" not in x, x
         assert x["value"] > 0 and x["gpu_launches"] > 0 and x["e2e"]["first_call_ms"] > 0 and x["roofline"]["kernel_launches_per_step"] > 0
         assert x["cpu_baseline"].get("value", 0) > 0 and x["gpu_library_baseline"].get("value", 0) > 0, x
+
+
+def test_bench_config_datasets_follow_the_reference_split():
+    """bench_configs: the synthetic C2-shaped data set and its array restatement of data/split.py + data/convert.py — every user and
+    item keeps a record (the reference's id2item covers every row of the tables), warm records 8:1:1 with val / test users and items
+    all present in train, cold items disjoint from train and split by item, overall = cold + warm over users present in both."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench_configs as B
+    c = B.CONFIGS["C2"]
+    rng = np.random.default_rng(c["seed"])
+    pairs = B.synth_pairs(rng, c["n_users"], c["n_items"], c["n_inter"], c["zipf"])
+    assert len(pairs) == c["n_inter"] and len(np.unique(pairs[:, 0] * c["n_items"] + pairs[:, 1])) == c["n_inter"]
+    assert len(np.unique(pairs[:, 0])) == c["n_users"] and len(np.unique(pairs[:, 1])) == c["n_items"]
+    s, info = B.split_item_cold(rng, pairs, c["n_users"], c["n_items"])
+    tr_u, tr_i = set(s["training"][:, 0].tolist()), set(s["training"][:, 1].tolist())
+    for k in ("warm_valid", "warm_test"):
+        assert set(s[k][:, 0].tolist()) <= tr_u and set(s[k][:, 1].tolist()) <= tr_i
+    cold_items = set(info["cold_item"].tolist())
+    assert not (cold_items & tr_i) and abs(len(cold_items) / c["n_items"] - 0.2) < 0.01
+    assert not (set(s["cold_valid"][:, 1].tolist()) & set(s["cold_test"][:, 1].tolist()))
+    for k, (cold, warm) in {"overall_valid": ("cold_valid", "warm_valid"), "overall_test": ("cold_test", "warm_test")}.items():
+        both = set(s[cold][:, 0].tolist()) & set(s[warm][:, 0].tolist())
+        assert set(s[k][:, 0].tolist()) == both
+    n_warm = len(s["training"]) + len(s["warm_valid"]) + len(s["warm_test"])
+    assert n_warm + len(s["cold_valid"]) + len(s["cold_test"]) == c["n_inter"]
+    assert abs(len(s["training"]) / n_warm - 0.8) < 0.05
+    data, _ = B.make_dataset("C2")
+    assert data.training_size()[:2] == (c["n_users"], c["n_items"]) and len(data.id2item) == c["n_items"]
