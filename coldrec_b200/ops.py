@@ -252,6 +252,9 @@ def copy_rows(src: torch.Tensor, dst: torch.Tensor, src_ids=None, dst_ids=None) 
 
 
 # ------------------------------------------------------------------------------------------------ K2
+_DCG_TABLES = {}
+
+
 def dcg_tables(K: int):
     """1/log(n+2,2) and its running sums, computed with the reference's own expression and addition
     order (util/evaluator.py:104-109) so device-side DCG/IDCG match it bit for bit."""
@@ -276,8 +279,10 @@ def rank_metrics(topk_id: torch.Tensor, gt_rowptr: torch.Tensor, gt_col: torch.T
     if gt_rowptr.numel() != n_q + 1:
         raise ValueError("gt_rowptr must have n_q+1 entries")
     nN = len(Ns)
-    inv, pre = dcg_tables(K)
-    tab = torch.tensor(inv + pre, dtype=torch.float64, device=dev)
+    tab = _DCG_TABLES.get((K, dev))
+    if tab is None:                  # constants of (K): uploaded once per device, not once per evaluation (a synchronous pageable copy)
+        inv, pre = dcg_tables(K)
+        tab = _DCG_TABLES[(K, dev)] = torch.tensor(inv + pre, dtype=torch.float64, device=dev)
     sums = torch.empty((nN, 6), dtype=torch.float64, device=dev)
     hits = torch.empty((nN, n_q), dtype=torch.int32, device=dev) if per_query else None
     dcg = torch.empty((nN, n_q), dtype=torch.float64, device=dev) if per_query else None
